@@ -1,0 +1,51 @@
+"""The oracle (numpy restatement) replayed against every golden vector produced by the unmodified reference.
+
+Runs on CPU (``-m "not gpu"``).  In the container that generated the goldens the match is bit for bit (same
+numpy/scipy/OpenBLAS calls in the same order); across machines OpenBLAS may split ``ddot`` differently, so the
+assertion is a tight relative tolerance for CG/MrR/small k and count-level for large k."""
+import numpy as np
+import pytest
+
+import krylov_oracle as oracle
+from golden_util import CASES, history_tolerance, inputs, load
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_oracle_matches_reference_golden(case):
+    gold = load(case)
+    mat, b = inputs(case)
+    kwargs = {"tol": case["tol"], "maxiter": case["maxiter"]}
+    if case["k"] is not None:
+        kwargs["k"] = case["k"]
+    x, info = oracle.SOLVERS[case["solver"]](mat, b.copy(), **kwargs)
+    tol = history_tolerance(case)
+    if tol is not None:
+        assert np.array_equal(info["nosl"], gold["nosl"])
+        np.testing.assert_allclose(info["residual"], gold["residual"], rtol=1e-11, atol=0)
+        if "x" in gold:
+            np.testing.assert_allclose(x, gold["x"], rtol=1e-9, atol=1e-12 * np.abs(gold["x"]).max())
+        else:
+            np.testing.assert_allclose(np.linalg.norm(x), gold["x_norm"], rtol=1e-10)
+    else:
+        assert abs(int(info["nosl"][-1]) - int(gold["nosl"][-1])) <= max(2, 0.05 * gold["nosl"][-1]) or \
+            np.array_equal(info["nosl"], gold["nosl"])
+    if "khistory" in gold and tol is not None:
+        assert np.array_equal(info["khistory"], gold["khistory"])
+    if case["final_residual"] < case["tol"]:
+        assert oracle.true_relres(mat, b, x) < 1.05 * case["tol"]
+
+
+def test_oracle_is_bitwise_on_generating_machine():
+    """Same machine, same libraries ⇒ identical bits (guards against the restatement drifting)."""
+    same = 0
+    for case in CASES[:40]:
+        gold = load(case)
+        mat, b = inputs(case)
+        kwargs = {"tol": case["tol"], "maxiter": case["maxiter"]}
+        if case["k"] is not None:
+            kwargs["k"] = case["k"]
+        _, info = oracle.SOLVERS[case["solver"]](mat, b.copy(), **kwargs)
+        if len(info["residual"]) == len(gold["residual"]) and np.array_equal(info["residual"], gold["residual"]):
+            same += 1
+    # OpenBLAS threading differs between hosts; require the overwhelming majority, not all.
+    assert same >= 30, same
