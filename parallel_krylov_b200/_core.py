@@ -1,0 +1,348 @@
+"""Host side of the drop-in boundary: buffers are torch CUDA tensors, compute is libpkrylov (ctypes).
+
+Mirrors the helper layer of the reference (``init`` / ``MultiGpu`` in /root/reference/v3/gpu/common.py:25-126):
+``Context`` ≙ ``MultiGpu.init`` (one device, one stream), ``Operator`` ≙ ``MultiGpu.alloc`` (A uploaded once, kernel
+chosen from its nnz distribution), ``solve`` ≙ the body of the five v3 solver functions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PkError, SolveOpts, SolveResult, check
+
+HIST_CAP = 1 << 22   # history entries kept on the device when maxiter is larger (the reference allocates maxiter+1)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise PkError("parallel_krylov_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+class Context:
+    """One per device: stream, reduction scratch, device-resident solver state, optional NCCL communicator."""
+
+    _by_device: dict = {}
+
+    def __init__(self, device: int):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.pk_ctx_create(C.byref(h), self.device, C.c_void_p(0)), "pk_ctx_create")
+        self.handle = h
+        self.n_ranks = 1
+        self.rank = 0
+        self.group = None
+
+    @classmethod
+    def get(cls, device: Optional[int] = None) -> "Context":
+        _require_cuda()
+        if device is None:
+            device = torch.cuda.current_device()
+        device = int(device)
+        if device not in cls._by_device:
+            cls._by_device[device] = Context(device)
+        return cls._by_device[device]
+
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.device)
+
+    def sync(self):
+        check(self.lib.pk_ctx_sync(self.handle), "pk_ctx_sync")
+
+    # -- communicator ---------------------------------------------------------------------------------------
+    def init_comm(self, group=None):
+        """Create the NCCL communicator libpkrylov uses, bootstrapped over an existing torch.distributed group
+        (≙ ``MultiGpu.joint_mpi(comm)``, /root/reference/v3/gpu/mpi/common.py:168-171)."""
+        import torch.distributed as dist
+        if self.n_ranks > 1:
+            return
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        if world == 1:
+            return
+        path = _find_nccl().encode()
+        idbuf = C.create_string_buffer(_lib.PK_NCCL_ID_BYTES)
+        if rank == 0:
+            check(self.lib.pk_nccl_unique_id(path, idbuf), "pk_nccl_unique_id")
+        backend = dist.get_backend(group)
+        dev = self.torch_device if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().tolist())
+        with torch.cuda.device(self.device):
+            check(self.lib.pk_comm_init(self.handle, path, world, rank, raw), "pk_comm_init")
+        self.n_ranks, self.rank, self.group = world, rank, group
+
+
+def _find_nccl() -> str:
+    """The libnccl torch already mapped into this process (so both share one NCCL), else the wheel's copy."""
+    try:
+        with open("/proc/self/maps") as fh:
+            for line in fh:
+                if "libnccl" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import nvidia.nccl as nn
+        cand = os.path.join(os.path.dirname(nn.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class Operator:
+    """A (row block of) A resident in HBM: CSR (int32 indices, fp64 values) or dense row-major fp64."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        self.n_rows = 0          # local rows
+        self.n_global = 0
+        self.row0 = 0
+        self.tensors = {}        # keeps the device arrays alive
+        self.kind = None
+        self.nnz = 0
+        self.h2d_bytes = 0
+        self.n_halo = 0
+        self.row_offsets = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.pk_mat_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def ld(self) -> int:
+        return int(self.ctx.lib.pk_mat_ld(self.handle))
+
+    def kernel_info(self):
+        k, r, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.ctx.lib.pk_mat_kernel_info(self.handle, C.byref(k), C.byref(r), C.byref(c)))
+        return {"kernel": ["csr-stream", "csr-vector", "dense-gemv"][k.value], "tile_rows": r.value,
+                "tile_cap": c.value}
+
+    # -- constructors -------------------------------------------------------------------------------------------
+    @classmethod
+    def from_csr_tensors(cls, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n_cols: int,
+                         ctx: Optional[Context] = None) -> "Operator":
+        ctx = ctx or Context.get(rowptr.device.index)
+        dev = ctx.torch_device
+        op = cls(ctx)
+        h2d = 0
+        def dv(t, dtype):
+            nonlocal h2d
+            if t.device != dev:
+                h2d += t.numel() * torch.empty((), dtype=dtype).element_size()
+            return t.to(device=dev, dtype=dtype).contiguous()
+        rowptr, col, val = dv(rowptr, torch.int32), dv(col, torch.int32), dv(val, torch.float64)
+        op.tensors = {"rowptr": rowptr, "col": col, "val": val}
+        op.n_rows = rowptr.numel() - 1
+        op.n_global = int(n_cols)
+        op.nnz = int(val.numel())
+        op.h2d_bytes = h2d
+        op.kind = "csr"
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_mat_csr(ctx.handle, C.byref(op.handle), op.n_rows, int(n_cols), op.nnz,
+                                     _ptr(rowptr), _ptr(col), _ptr(val)), "pk_mat_csr")
+        return op
+
+    @classmethod
+    def from_dense_tensor(cls, a: torch.Tensor, ctx: Optional[Context] = None) -> "Operator":
+        ctx = ctx or Context.get(a.device.index if a.is_cuda else None)
+        op = cls(ctx)
+        op.h2d_bytes = 0 if a.is_cuda else a.numel() * 8
+        a = a.to(device=ctx.torch_device, dtype=torch.float64).contiguous()
+        op.tensors = {"dense": a}
+        op.n_rows, op.n_global = int(a.shape[0]), int(a.shape[1])
+        op.nnz = a.numel()
+        op.kind = "dense"
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_mat_dense(ctx.handle, C.byref(op.handle), op.n_rows, op.n_global, _ptr(a),
+                                       int(a.stride(0))), "pk_mat_dense")
+        return op
+
+    @classmethod
+    def from_any(cls, A, ctx: Optional[Context] = None) -> "Operator":
+        """scipy sparse (any format) / numpy 2-D / torch dense or sparse-CSR / (rowptr, col, val, n) / Operator —
+        the inputs ``MultiGpu.alloc`` accepts (/root/reference/v3/gpu/common.py:100-104) plus device-resident ones."""
+        if isinstance(A, Operator):
+            return A
+        ctx = ctx or Context.get()
+        if isinstance(A, np.ndarray):
+            if A.ndim != 2:
+                raise PkError("dense A must be 2-D")
+            return cls.from_dense_tensor(torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64)), ctx)
+        if isinstance(A, torch.Tensor):
+            if A.layout == torch.sparse_csr:
+                return cls.from_csr_tensors(A.crow_indices(), A.col_indices(), A.values(), A.shape[1], ctx)
+            return cls.from_dense_tensor(A, ctx)
+        if isinstance(A, (tuple, list)) and len(A) == 4:
+            rp, ci, va, n = A
+            as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            return cls.from_csr_tensors(as_t(rp), as_t(ci), as_t(va), int(n), ctx)
+        if hasattr(A, "tocsr"):
+            m = A.tocsr()
+            if not m.has_sorted_indices:
+                m = m.sorted_indices()
+            return cls.from_csr_tensors(torch.from_numpy(np.ascontiguousarray(m.indptr)),
+                                        torch.from_numpy(np.ascontiguousarray(m.indices)),
+                                        torch.from_numpy(np.ascontiguousarray(m.data, dtype=np.float64)),
+                                        m.shape[1], ctx)
+        raise PkError(f"unsupported matrix type {type(A)!r}")
+
+    # -- building blocks (tests / benchmarks) ------------------------------------------------------------------
+    def matvec(self, x: torch.Tensor, dot_with: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None):
+        """y = A x through the solver's operator kernel.  Returns y (and y1), plus the fused sums when asked."""
+        ctx = self.ctx
+        ld = self.ld
+        def padded(v):
+            buf = torch.zeros(ld, dtype=torch.float64, device=ctx.torch_device)
+            buf[: v.numel()] = v.to(ctx.torch_device, torch.float64)
+            return buf
+        xb = padded(x)
+        x1b = padded(x1) if x1 is not None else None
+        y = torch.empty(ld, dtype=torch.float64, device=ctx.torch_device)
+        y1 = torch.empty(ld, dtype=torch.float64, device=ctx.torch_device) if x1 is not None else None
+        w = dot_with.to(ctx.torch_device, torch.float64).contiguous() if dot_with is not None else None
+        sums = torch.zeros(3, dtype=torch.float64, device=ctx.torch_device)
+        torch.cuda.current_stream(ctx.device).synchronize()
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_spmv(ctx.handle, self.handle, _ptr(xb), _ptr(y), _ptr(x1b), _ptr(y1), _ptr(w),
+                                  _ptr(sums)), "pk_spmv")
+        ctx.sync()
+        out = [y[: self.n_rows]]
+        if x1 is not None:
+            out.append(y1[: self.n_rows])
+        if dot_with is not None:
+            out.append(sums)
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _banner_start(name: str, k):
+    # same fields as the reference banner (/root/reference/v3/common.py:2-6)
+    print("# " + "=" * 16 + " INFO " + "=" * 16 + " #")
+    print(f"Method:\t\t{name}")
+    if k is not None:
+        print(f"Initial_k:\t{k}")
+
+
+def _banner_finish(elapsed, converged, iters, final_res, final_k=None):
+    # /root/reference/v3/common.py:9-23
+    print(f"Time:\t\t{elapsed} s")
+    print(f"Status:\t\t{'converged' if converged else 'diverged'}")
+    print(f"Iteration:\t{iters} times")
+    print(f"Final_Residual:\t{final_res}")
+    if final_k:
+        print(f"Final_k:\t{final_k}")
+    print("# " + "=" * 38 + " #")
+
+
+_NAMES = {"cg": "CG", "mrr": "MrR", "kskipcg": "k-skip CG", "kskipmrr": "k-skip MrR",
+          "adaptivekskipmrr": "Adaptive k-skip MrR"}
+
+
+def quiet() -> bool:
+    return os.environ.get("PK_QUIET", "0") not in ("0", "")
+
+
+def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_every: int = 0,
+          use_graph: Optional[bool] = None, verbose: Optional[bool] = None, ctx: Optional[Context] = None):
+    """Shared body of the five entry points.  Returns ``(x, info)`` like the reference
+    (/root/reference/v3/gpu/cg.py:47-52): x and the histories are torch CUDA tensors."""
+    op = Operator.from_any(A, ctx)
+    ctx = op.ctx
+    dev = ctx.torch_device
+    lib = ctx.lib
+    n = op.n_rows
+    if op.n_global != n and op.n_halo == 0 and op.kind != "dense":
+        raise PkError(f"A must be square (got {n} x {op.n_global}); use parallel_krylov_b200.mpi for row blocks")
+    ld = op.ld
+
+    # init(): /root/reference/v3/gpu/common.py:25-40
+    h2d = op.h2d_bytes
+    if isinstance(b, np.ndarray):
+        h2d += b.size * 8
+        b_t = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(dev)
+    else:
+        if not b.is_cuda:
+            h2d += b.numel() * 8
+        b_t = b.to(device=dev, dtype=torch.float64).contiguous()
+    if b_t.numel() != n:
+        raise PkError(f"b has {b_t.numel()} entries, A has {n} rows")
+    x_t = torch.zeros(ld, dtype=torch.float64, device=dev)
+    x_is_zero = True
+    if isinstance(x, np.ndarray):           # only an ndarray counts as an initial guess (v3/gpu/common.py:30-33)
+        x_t[:n] = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+        h2d += x.size * 8
+        x_is_zero = False
+    elif isinstance(x, torch.Tensor):
+        x_t[:n] = x.to(device=dev, dtype=torch.float64)
+        x_is_zero = False
+    if maxiter is None:
+        maxiter = op.n_global               # v3/gpu/common.py:35-36
+    maxiter = int(maxiter)
+    k = int(k)
+    if not 0 <= k <= _lib.PK_KMAX:
+        raise PkError(f"k must be in 0..{_lib.PK_KMAX}")
+    mid = _lib.METHOD_IDS[method]
+    hist_len = min(maxiter + k + 3, max(HIST_CAP, 4))
+    residual = torch.zeros(hist_len, dtype=torch.float64, device=dev)
+    nosl = torch.zeros(hist_len, dtype=torch.int64, device=dev)
+    khist = torch.zeros(hist_len, dtype=torch.int64, device=dev) if method == "adaptivekskipmrr" else None
+    nwork = int(lib.pk_work_doubles(mid, ld, k))
+    work = torch.zeros(nwork, dtype=torch.float64, device=dev)
+
+    opts = SolveOpts(maxiter=maxiter, tol=float(tol), k=k, check_every=int(check_every),
+                     use_graph=1 if (use_graph if use_graph is not None else True) else 0,
+                     x_is_zero=1 if x_is_zero else 0, global_n=op.n_global)
+    res = SolveResult()
+    show = (not quiet()) if verbose is None else verbose
+    if show and ctx.rank == 0:
+        _banner_start(_NAMES[method], k if method.startswith(("kskip", "adaptive")) else None)
+    torch.cuda.current_stream(ctx.device).synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.device(ctx.device):
+        check(lib.pk_solve(ctx.handle, mid, op.handle, _ptr(b_t), _ptr(x_t), _ptr(work), _ptr(residual), _ptr(nosl),
+                           _ptr(khist), hist_len, C.byref(opts), C.byref(res)), f"pk_solve({method})")
+    wall = time.perf_counter() - t0
+    entries = int(min(res.entries, hist_len))
+    if show and ctx.rank == 0:
+        _banner_finish(res.elapsed_s, bool(res.converged), int(res.iterations), res.final_residual,
+                       res.final_k if method == "adaptivekskipmrr" else None)
+    info = {
+        "time": res.elapsed_s,                 # loop time (CUDA events), the reference's timer placement
+        "nosl": nosl[:entries],
+        "residual": residual[:entries],
+        # extras (not in the reference's dict)
+        "converged": bool(res.converged),
+        "iterations": int(res.iterations),
+        "wall_time": wall,
+        "gpu_launches": int(res.kernel_launches),
+        "spmv": int(res.spmv_count),
+        "h2d_bytes": int(h2d),
+    }
+    if method == "adaptivekskipmrr":
+        info["khistory"] = khist[:entries]
+        info["final_k"] = int(res.final_k)
+    return x_t[:n], info

@@ -1,0 +1,247 @@
+// Device-side helpers: deterministic block/grid reductions with a last-block epilogue, and the scalar engine
+// (every scalar recurrence of the reference loops, executed by one thread on the reduced sums).
+#pragma once
+#include "pk_common.cuh"
+
+struct PkRedArgs {
+    double* partials;       // [nsums][max_blocks]
+    unsigned int* ticket;
+    int max_blocks;
+    PkState* st;
+    int epi;                // PkEpi
+    int defer;              // 1: only publish the sums (multi-GPU: all-reduce + pk_scalar_kernel follow)
+    int g_off;              // >= 0: publish into st->gram[g_off + j] instead of st->red[j]
+    // split launches that feed ONE reduction (interior rows, then boundary rows after the halo arrived):
+    int block_off;          // this launch's partials start at this block slot
+    int nb_total;           // slots the final reduction covers (0: gridDim.x)
+    int store_only;         // 1: just store the partials (a later launch on the same stream finishes)
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// Rounding discipline: the library is compiled with -fmad=false so that a*b+c rounds twice exactly like numpy's
+// temporaries (`x += alpha * p` is a multiply then an add, /root/reference/v3/cpu/cg.py:30).
+
+__device__ __forceinline__ void pk_record(PkState* st, long long idx, long long it, double res, bool with_k) {
+    if (idx < st->hist_len) {
+        st->res[idx] = res;
+        st->nosl[idx] = it;
+        if (with_k && st->khist) st->khist[idx] = st->k;
+    }
+}
+
+__device__ __forceinline__ void pk_stop_test(PkState* st, double res) {
+    // `while i < maxiter:` is evaluated before `if residual[i] < tol` (v3/cpu/cg.py:19-24): reaching the cap ends
+    // the loop as "not converged" even when the last residual is below tol.
+    if (st->it < st->maxiter) {
+        if (res < st->tol) {
+            st->converged = 1;
+            st->done = 1;
+        }
+    } else {
+        st->converged = 0;
+        st->done = 1;
+    }
+}
+
+// All k+1 (alpha_j, beta_j) of a k-skip CG trip from the Gram sums — v3/cpu/kskipcg.py:51-52, :59-68.
+__device__ inline void pk_kskipcg_scalars(PkState* st) {
+    const int k = st->k;
+    const double* G = st->gram;
+    double a[2 * PK_KMAX + 2], f[2 * PK_KMAX + 4], c[2 * PK_KMAX + 2];
+    for (int j = 0; j < 2 * k + 1; ++j) a[j] = G[6 * (j >> 1) + (j & 1)];
+    a[2 * k + 1] = 0.0;
+    for (int j = 0; j < 2 * k + 4; ++j) f[j] = G[6 * (j >> 1) + 4 + (j & 1)];
+    for (int j = 0; j < 2 * k + 2; ++j) c[j] = G[6 * (j >> 1) + 2 + (j & 1)];
+    double alpha = a[0] / f[1];
+    double beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
+    st->coef[0] = alpha;
+    st->coef[1] = beta;
+    for (int j = 0; j < k; ++j) {
+        for (int l = 0; l < 2 * (k - j) + 1; ++l) {
+            a[l] = a[l] + alpha * (alpha * f[l + 2] - 2.0 * c[l + 1]);
+            double d = c[l] - alpha * f[l + 1];
+            c[l] = a[l] + d * beta;
+            f[l] = c[l] + beta * (d + beta * f[l]);
+        }
+        alpha = a[0] / f[1];
+        beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
+        st->coef[2 * (j + 1)] = alpha;
+        st->coef[2 * (j + 1) + 1] = beta;
+    }
+}
+
+// All k+1 (zeta_j, eta_j) of a k-skip MrR trip — v3/cpu/kskipmrr.py:62-64, :72-88.
+__device__ inline void pk_kskipmrr_scalars(PkState* st) {
+    const int k = st->k;
+    const double* G = st->gram;
+    double al[2 * PK_KMAX + 3], be[2 * PK_KMAX + 2], de[2 * PK_KMAX + 1];
+    for (int j = 0; j < 2 * k + 3; ++j) al[j] = G[6 * (j >> 1) + (j & 1)];
+    be[0] = 0.0;
+    for (int j = 1; j < 2 * k + 2; ++j) be[j] = G[6 * (j >> 1) + 2 + (j & 1)];
+    for (int j = 0; j < 2 * k + 1; ++j) de[j] = G[6 * (j >> 1) + 4 + (j & 1)];
+    double d = al[2] * de[0] - be[1] * be[1];
+    double zeta = (al[1] * de[0]) / d;
+    double eta = ((-al[1]) * be[1]) / d;
+    st->coef[0] = zeta;
+    st->coef[1] = eta;
+    for (int j = 0; j < k; ++j) {
+        de[0] = (zeta * zeta) * al[2] + (eta * zeta) * be[1];
+        al[0] = al[0] - zeta * al[1];
+        de[1] = ((eta * eta) * de[1] + ((2.0 * eta) * zeta) * be[2]) + (zeta * zeta) * al[3];
+        be[1] = (eta * be[1] + zeta * al[2]) - de[1];
+        al[1] = -be[1];
+        for (int l = 2; l < 2 * (k - j) + 1; ++l) {
+            de[l] = ((eta * eta) * de[l] + ((2.0 * eta) * zeta) * be[l + 1]) + (zeta * zeta) * al[l + 2];
+            double tau = eta * be[l] + zeta * al[l + 1];
+            be[l] = tau - de[l];
+            al[l] = al[l] - (tau + be[l]);
+        }
+        d = al[2] * de[0] - be[1] * be[1];
+        zeta = (al[1] * de[0]) / d;
+        eta = ((-al[1]) * be[1]) / d;
+        st->coef[2 * (j + 1)] = zeta;
+        st->coef[2 * (j + 1) + 1] = eta;
+    }
+}
+
+// The scalar engine.  `st->red` (or st->gram) already holds the fully reduced sums.
+template <bool GRAM>
+__device__ inline void pk_epilogue(int epi, PkState* st) {
+    const double* s = st->red;
+    switch (epi) {
+        case EPI_BNORM:
+            st->bnorm = sqrt(s[0]);
+            break;
+        case EPI_CG_INIT: {               // v3/cpu/cg.py:14, :21-24 (first pass)
+            st->gamma = s[0];
+            st->rr = s[0];
+            double res = sqrt(s[0]) / st->bnorm;
+            st->it = 0;
+            st->idx = 0;
+            pk_record(st, 0, 0, res, false);
+            pk_stop_test(st, res);
+            break;
+        }
+        case EPI_CG_ALPHA:                // v3/cpu/cg.py:28-29
+            st->alpha = st->gamma / s[0];
+            break;
+        case EPI_CG_BETA: {               // v3/cpu/cg.py:32-37, then :21-24 of the next pass
+            double g = s[0];
+            st->beta = g / st->gamma;
+            st->gamma = g;
+            st->rr = g;
+            st->it += 1;
+            st->idx = st->it;
+            double res = sqrt(g) / st->bnorm;
+            pk_record(st, st->it, st->it, res, false);
+            pk_stop_test(st, res);
+            break;
+        }
+        case EPI_RES0: {                  // v3/cpu/mrr.py:13 — recorded, not tested
+            st->rr = s[0];
+            st->it = 0;
+            st->idx = 0;
+            pk_record(st, 0, 0, sqrt(s[0]) / st->bnorm, true);
+            break;
+        }
+        case EPI_MRR_FIRST:               // v3/cpu/mrr.py:19   zeta = (r.Ar)/(Ar.Ar)
+            st->zeta = s[0] / s[1];
+            break;
+        case EPI_KS_FIRST:                // opening step done: i = 1, index = 1 (v3/cpu/mrr.py:24-25, kskipmrr.py:32-34)
+        case EPI_MRR_STEP: {              // v3/cpu/mrr.py:49-50 then :30-33
+            st->rr = s[0];
+            st->it += 1;
+            st->idx = st->it;
+            double res = sqrt(s[0]) / st->bnorm;
+            pk_record(st, st->it, st->it, res, true);
+            pk_stop_test(st, res);
+            break;
+        }
+        case EPI_MRR_GAMMA:               // v3/cpu/mrr.py:37-39  mu = y.y, nu = y.Ar
+            st->nu = s[0];
+            st->mu = s[2];
+            st->gamma = s[0] / s[2];
+            break;
+        case EPI_MRR_ZETA:                // v3/cpu/mrr.py:41-44
+            st->zeta = s[0] / s[1];
+            st->eta = (-st->zeta) * st->gamma;
+            break;
+        case EPI_KS_TRIP_END: {           // v3/cpu/kskipcg.py:74-76 / kskipmrr.py:95-97, then the loop-top test
+            st->rr = s[0];
+            st->it += st->k + 1;
+            st->idx += 1;
+            double res = sqrt(s[0]) / st->bnorm;
+            pk_record(st, st->idx, st->it, res, true);
+            pk_stop_test(st, res);
+            break;
+        }
+        case EPI_ADAPT_STEP: {            // v3/cpu/adaptivekskipmrr.py:58-61 (rollback step; host lowers k)
+            st->rr = s[0];
+            st->it += 1;
+            st->idx += 1;
+            pk_record(st, st->idx, st->it, sqrt(s[0]) / st->bnorm, false);
+            break;
+        }
+        case EPI_GRAM_CG:
+            if (GRAM) pk_kskipcg_scalars(st);   // only the Gram kernel / scalar kernel carry the recurrence stack
+            break;
+        case EPI_GRAM_MRR:
+            if (GRAM) pk_kskipmrr_scalars(st);
+            break;
+        default:
+            break;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Block reduction of NS running sums (fixed shape: shuffle tree, then warps in order), one partial per block,
+// then the last block to finish (ticket) reduces the partials in a fixed order and runs the epilogue.
+// Deterministic for a given grid size; no floating-point atomics anywhere.
+template <int NS, int BLOCK, bool GRAM = false>
+__device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArgs& ra) {
+    constexpr int NW = BLOCK / 32;
+    __shared__ double sh[NS][NW];
+    __shared__ double tot[NS];
+    __shared__ int is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double v = acc[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[j][warp] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < NS; j += BLOCK) {
+        double v = sh[j][0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) v += sh[j][w];
+        ra.partials[(size_t)j * ra.max_blocks + ra.block_off + blockIdx.x] = v;
+        __threadfence();
+    }
+    if (ra.store_only) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ra.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nb = ra.nb_total > 0 ? ra.nb_total : (int)gridDim.x;
+    for (int j = warp; j < NS; j += NW) {
+        const double* p = ra.partials + (size_t)j * ra.max_blocks;
+        double v = 0.0;
+        for (int b = lane; b < nb; b += 32) v += __ldcg(p + b);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) tot[j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ra.ticket = 0u;
+        double* dst = (ra.g_off >= 0) ? (ra.st->gram + ra.g_off) : ra.st->red;
+        for (int j = 0; j < NS; ++j) dst[j] = tot[j];
+        if (!ra.defer) pk_epilogue<GRAM>(ra.epi, ra.st);
+    }
+}

@@ -1,0 +1,350 @@
+// Fused vector kernels of the solver loops (K3 of SURVEY.md §2b), the single-pass Gram kernel (K4) and the
+// scalar engine launch (K5).  All are HBM-bound streaming kernels: one pass, no temporaries, the dot products
+// the next step needs are reduced in the same pass (warp shuffle -> block -> last block).
+#include "pk_device.cuh"
+#include "pk_launch.h"
+
+namespace {
+
+constexpr int EW_BLOCK = 256;
+
+__device__ __forceinline__ bool pk_done(const PkState* st) { return *((volatile const int*)&st->done) != 0; }
+
+// ---- dot ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_BLOCK) k_dot(long long n, const double* __restrict__ u,
+                                                  const double* __restrict__ v, PkRedArgs ra, int ignore_done) {
+    if (!ignore_done && pk_done(ra.st)) return;
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) acc[0] += u[i] * v[i];
+    pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- r = b - v (or r = b), optional p = r, sums[0] = r.r  — v3/cpu/cg.py:12-14, mrr.py:12-13 --------------------
+__global__ void __launch_bounds__(EW_BLOCK) k_resid_init(long long n, const double* __restrict__ b,
+                                                         const double* __restrict__ v, double* __restrict__ r,
+                                                         double* __restrict__ p, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double ri = v ? (b[i] - v[i]) : b[i];
+        r[i] = ri;
+        if (p) p[i] = ri;
+        acc[0] += ri * ri;
+    }
+    pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- CG: x += alpha p ; r -= alpha v ; sums[0] = r.r  — v3/cpu/cg.py:30-33 --------------------------------------
+__global__ void __launch_bounds__(EW_BLOCK) k_cg_xr(long long n, double* __restrict__ x, double* __restrict__ r,
+                                                    const double* __restrict__ p, const double* __restrict__ v,
+                                                    PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    const double alpha = ra.st->alpha;
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        x[i] = x[i] + alpha * p[i];
+        double ri = r[i] - alpha * v[i];
+        r[i] = ri;
+        acc[0] += ri * ri;
+    }
+    pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- CG: p = r + beta p  — v3/cpu/cg.py:35 -----------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_BLOCK) k_cg_p(long long n, double* __restrict__ p, const double* __restrict__ r,
+                                                   const PkState* st) {
+    if (pk_done(st)) return;
+    const double beta = st->beta;
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) p[i] = r[i] + beta * p[i];
+}
+
+// ---- MrR opening step: y = zeta Ar ; z = -zeta r ; r -= y ; x -= z ; sums[0] = r.r  — v3/cpu/mrr.py:20-23 --------
+__global__ void __launch_bounds__(EW_BLOCK) k_mrr_first(long long n, const double* __restrict__ ar,
+                                                        double* __restrict__ r, double* __restrict__ x,
+                                                        double* __restrict__ y, double* __restrict__ z, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    const double zeta = ra.st->zeta;
+    const double nzeta = -zeta;
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double yi = zeta * ar[i];
+        double zi = nzeta * r[i];
+        double ri = r[i] - yi;
+        y[i] = yi;
+        z[i] = zi;
+        r[i] = ri;
+        x[i] = x[i] - zi;
+        acc[0] += ri * ri;
+    }
+    pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- MrR: s = Ar - gamma y ; sums = {r.s, s.s}  — v3/cpu/mrr.py:40-42 (s is never stored) -----------------------
+__global__ void __launch_bounds__(EW_BLOCK) k_mrr_s(long long n, const double* __restrict__ ar,
+                                                    const double* __restrict__ y, const double* __restrict__ r,
+                                                    PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    const double gamma = ra.st->gamma;
+    double acc[2] = {0.0, 0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double s = ar[i] - gamma * y[i];
+        acc[0] += r[i] * s;
+        acc[1] += s * s;
+    }
+    pk_grid_reduce<2, EW_BLOCK>(acc, ra);
+}
+
+// ---- MrR step: y = eta y + zeta Ar ; z = eta z - zeta r ; r -= y ; x -= z ; sums[0] = r.r -----------------------
+//      v3/cpu/mrr.py:45-48 ; kskipmrr.py:65-69 / :89-93 with (zeta, eta) = coef[2j], coef[2j+1]
+__global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const double* __restrict__ ar,
+                                                         double* __restrict__ y, double* __restrict__ z,
+                                                         double* __restrict__ r, double* __restrict__ x, int cj,
+                                                         PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    const double zeta = (cj < 0) ? ra.st->zeta : ra.st->coef[2 * cj];
+    const double eta = (cj < 0) ? ra.st->eta : ra.st->coef[2 * cj + 1];
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double ri = r[i];
+        double yi = eta * y[i] + zeta * ar[i];
+        double zi = eta * z[i] - zeta * ri;
+        ri = ri - yi;
+        y[i] = yi;
+        z[i] = zi;
+        r[i] = ri;
+        x[i] = x[i] - zi;
+        acc[0] += ri * ri;
+    }
+    if (ra.epi != EPI_KS_STEP) pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- k-skip CG step: x += a Ap0 ; Ar0 -= a Ap1 ; Ap0 = Ar0 + b Ap0 ; sums[0] = Ar0.Ar0  — kskipcg.py:53-55 -----
+__global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* __restrict__ x,
+                                                          double* __restrict__ ar0, double* __restrict__ ap0,
+                                                          const double* __restrict__ ap1, int cj, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    const double alpha = ra.st->coef[2 * cj];
+    const double beta = ra.st->coef[2 * cj + 1];
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double p0 = ap0[i];
+        x[i] = x[i] + alpha * p0;
+        double ri = ar0[i] - alpha * ap1[i];
+        ar0[i] = ri;
+        ap0[i] = ri + beta * p0;
+        acc[0] += ri * ri;
+    }
+    if (ra.epi != EPI_KS_STEP) pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- Gram window: all pair products for jj in [j0, j0+W) in one pass over the basis ------------------------------
+// U rows [0,nu), V rows [0,nv), row stride ld.  Per jj six sums (see pkrylov.h: pk_gram).  Rows that do not exist
+// contribute zeros (their loads are skipped; the predicate is uniform across the grid).
+template <int W, int MODE>
+__global__ void __launch_bounds__(EW_BLOCK) k_gram(long long n, long long ld, const double* __restrict__ U, int nu,
+                                                   const double* __restrict__ V, int nv, int j0, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    double acc[6 * W];
+#pragma unroll
+    for (int t = 0; t < 6 * W; ++t) acc[t] = 0.0;
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double u[W + 1], v[W + 1];
+#pragma unroll
+        for (int t = 0; t <= W; ++t) {
+            u[t] = (j0 + t < nu) ? U[(long long)(j0 + t) * ld + i] : 0.0;
+            v[t] = (j0 + t < nv) ? V[(long long)(j0 + t) * ld + i] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            acc[6 * t + 0] += u[t] * u[t];
+            acc[6 * t + 1] += u[t] * u[t + 1];
+            acc[6 * t + 2] += u[t] * v[t];
+            acc[6 * t + 3] += (MODE == 0) ? (v[t] * u[t + 1]) : (u[t] * v[t + 1]);
+            acc[6 * t + 4] += v[t] * v[t];
+            acc[6 * t + 5] += v[t] * v[t + 1];
+        }
+    }
+    pk_grid_reduce<6 * W, EW_BLOCK, true>(acc, ra);
+}
+
+__global__ void k_scalar(PkState* st, int epi, int ignore_done) {
+    if (!ignore_done && pk_done(st)) return;
+    pk_epilogue<true>(epi, st);
+}
+
+__global__ void k_set_k(PkState* st, int k) {
+    st->k = k;
+    if (st->khist && st->idx < st->hist_len) st->khist[st->idx] = k;   // adaptivekskipmrr.py:66
+}
+
+inline int ew_grid(pk_ctx* ctx, long long n) {
+    long long want = (n + EW_BLOCK * 4 - 1) / (EW_BLOCK * 4);
+    long long cap = (long long)ctx->sm_count * 8;
+    if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
+    PkRedArgs ra;
+    ra.partials = ctx->red.partials;
+    ra.ticket = ctx->red.ticket;
+    ra.max_blocks = ctx->red.max_blocks;
+    ra.st = ctx->d_state;
+    ra.epi = epi;
+    ra.defer = ctx->n_ranks > 1 ? 1 : 0;
+    ra.g_off = g_off;
+    ra.block_off = 0;
+    ra.nb_total = 0;
+    ra.store_only = 0;
+    return ra;
+}
+
+#define PK_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            pk_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return PK_ERR_CUDA;                                                                \
+        }                                                                                      \
+        ctx->launches++;                                                                       \
+    } while (0)
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+int pk_launch_scalar(pk_ctx* ctx, int epi, int ignore_done) {
+    k_scalar<<<1, 1, 0, ctx->stream>>>(ctx->d_state, epi, ignore_done);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+int pk_launch_set_k(pk_ctx* ctx, int k) {
+    k_set_k<<<1, 1, 0, ctx->stream>>>(ctx->d_state, k);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+// After a reducing kernel: single GPU -> nothing to do (the last block already ran the epilogue);
+// multi GPU -> all-reduce the published sums over NVLink, then run the scalar engine.
+int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done) {
+    if (ctx->n_ranks <= 1) return PK_OK;
+    double* buf = (g_off >= 0) ? (ctx->d_state->gram + g_off) : ctx->d_state->red;
+    PK_CHECK(pk_comm_allreduce(ctx, buf, nsums, ctx->stream));
+    if (epi != EPI_NONE && epi != EPI_GRAM_PART && epi != EPI_KS_STEP) return pk_launch_scalar(ctx, epi, ignore_done);
+    return PK_OK;
+}
+
+int pk_launch_dot(pk_ctx* ctx, long long n, const double* u, const double* v, int epi, int ignore_done) {
+    k_dot<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, u, v, red_args(ctx, epi), ignore_done);
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, epi, -1, ignore_done);
+}
+
+int pk_launch_resid_init(pk_ctx* ctx, long long n, const double* b, const double* v, double* r, double* p, int epi) {
+    k_resid_init<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, b, v, r, p, red_args(ctx, epi));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, epi, -1, 0);
+}
+
+int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v) {
+    k_cg_xr<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args(ctx, EPI_CG_BETA));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, EPI_CG_BETA, -1, 0);
+}
+
+int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r) {
+    k_cg_p<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, p, r, ctx->d_state);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
+                        int epi) {
+    k_mrr_first<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, r, x, y, z, red_args(ctx, epi));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, epi, -1, 0);
+}
+
+int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r) {
+    k_mrr_s<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args(ctx, EPI_MRR_ZETA));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
+}
+
+int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
+                         int cj, int epi) {
+    k_mrr_update<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args(ctx, epi));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, epi, -1, 0);
+}
+
+int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
+                          int epi) {
+    k_kscg_update<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args(ctx, epi));
+    PK_LAUNCH_CHECK();
+    return pk_finish_reduce(ctx, 1, epi, -1, 0);
+}
+
+namespace {
+template <int W, int MODE>
+int gram_window(pk_ctx* ctx, long long n, long long ld, const double* U, int nu, const double* V, int nv, int j0,
+                int epi) {
+    // register-heavy kernel (6W accumulators): fewer, fatter blocks
+    long long cap = (long long)ctx->sm_count * (W <= 4 ? 4 : 2);
+    long long want = (n + EW_BLOCK - 1) / EW_BLOCK;
+    if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
+    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    k_gram<W, MODE><<<grid, EW_BLOCK, 0, ctx->stream>>>(n, ld, U, nu, V, nv, j0, red_args(ctx, epi, 6 * j0));
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+template <int MODE>
+int gram_dispatch(pk_ctx* ctx, int w, long long n, long long ld, const double* U, int nu, const double* V, int nv,
+                  int j0, int epi) {
+    switch (w) {
+        case 1: return gram_window<1, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 2: return gram_window<2, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 3: return gram_window<3, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 4: return gram_window<4, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 5: return gram_window<5, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 6: return gram_window<6, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 7: return gram_window<7, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 8: return gram_window<8, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 9: return gram_window<9, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 10: return gram_window<10, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        default: pk_set_error("gram window %d unsupported", w); return PK_ERR_ARG;
+    }
+}
+}  // namespace
+
+// All Gram sums for jj = 0 .. njj-1 (njj = k+2), in ceil(njj/10) passes (one pass for k <= 8).
+// final_epi runs once everything is reduced (EPI_GRAM_CG / EPI_GRAM_MRR / EPI_NONE).
+int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const double* U, int nu, const double* V, int nv,
+                   int njj, int final_epi) {
+    constexpr int WMAX = 10;
+    int j0 = 0;
+    while (j0 < njj) {
+        int w = njj - j0 < WMAX ? njj - j0 : WMAX;
+        bool last = (j0 + w >= njj);
+        int epi = last ? final_epi : EPI_GRAM_PART;
+        if (mode == 0) PK_CHECK((gram_dispatch<0>(ctx, w, n, ld, U, nu, V, nv, j0, epi)));
+        else PK_CHECK((gram_dispatch<1>(ctx, w, n, ld, U, nu, V, nv, j0, epi)));
+        j0 += w;
+    }
+    if (ctx->n_ranks > 1) {
+        PK_CHECK(pk_comm_allreduce(ctx, ctx->d_state->gram, 6LL * njj, ctx->stream));
+        if (final_epi != EPI_NONE) PK_CHECK(pk_launch_scalar(ctx, final_epi, 0));
+    }
+    return PK_OK;
+}

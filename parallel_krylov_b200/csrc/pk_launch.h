@@ -1,0 +1,34 @@
+// Internal launch API shared by the translation units of libpkrylov (not part of the C-ABI).
+#pragma once
+#include "pk_common.cuh"
+
+// pk_kernels.cu — fused vector kernels; every reducing launch is followed (multi-GPU) by all-reduce + scalar engine
+int pk_launch_scalar(pk_ctx* ctx, int epi, int ignore_done);
+int pk_launch_set_k(pk_ctx* ctx, int k);
+int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done);
+int pk_launch_dot(pk_ctx* ctx, long long n, const double* u, const double* v, int epi, int ignore_done);
+int pk_launch_resid_init(pk_ctx* ctx, long long n, const double* b, const double* v, double* r, double* p, int epi);
+int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v);
+int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r);
+int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
+                        int epi);
+int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r);
+int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
+                         int cj, int epi);
+int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
+                          int epi);
+int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const double* U, int nu, const double* V, int nv,
+                   int njj, int final_epi);
+
+// pk_spmv.cu — operator application y = A x (optionally two right-hand sides), fused dot epilogue
+struct PkDots {
+    const double* w = nullptr;   // sums: [0] = w.y, [1] = y.y, [2] = w.w   (nullptr: no reduction)
+    int epi = EPI_NONE;
+};
+int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
+
+// pk_comm.cu — NCCL over NVLink
+int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s);
+int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s);
+int pk_comm_halo_start(pk_ctx* ctx, pk_mat* mat, double* x, double* x1);   // pack + send/recv on the side stream
+int pk_comm_halo_wait(pk_ctx* ctx);                                        // main stream waits for the exchange

@@ -1,0 +1,560 @@
+// C-ABI entry points and the host side of the five solver loops.  The host only ENQUEUES: every scalar, the residual
+// history and the stopping flag live on the device (PkState); the host polls the flag once per batch of iterations,
+// one batch behind the GPU, so the device never idles waiting for the host (the reference syncs every iteration:
+// `if residual[i] < tol` on a cupy scalar, /root/reference/v3/gpu/cg.py:26).  Kernels enqueued after the stopping
+// rule fired are no-ops, so x, the history and the iteration count are exactly those of the reference loop.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+#include "pk_common.cuh"
+#include "pk_launch.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void pk_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* pk_last_error(void) { return g_err; }
+extern "C" int pk_version(void) { return PK_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
+    PK_REQUIRE(out != nullptr, "null out");
+    PK_CUDA(cudaSetDevice(device));
+    pk_ctx* c = new pk_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    if (c->stream == nullptr) {
+        // A *blocking* stream: it orders itself against the legacy default stream (where torch runs by default), and,
+        // unlike the legacy stream, it can be captured into a CUDA graph.
+        PK_CUDA(cudaStreamCreate(&c->stream));
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    PK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        pk_set_error("libpkrylov is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+        delete c;
+        return PK_ERR_UNSUPPORTED;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->red.max_blocks = c->sm_count * 16;
+    PK_CUDA(cudaMalloc(&c->red.partials, sizeof(double) * (size_t)PK_MAX_SUMS * c->red.max_blocks));
+    PK_CUDA(cudaMalloc(&c->red.ticket, sizeof(unsigned int)));
+    PK_CUDA(cudaMemset(c->red.ticket, 0, sizeof(unsigned int)));
+    PK_CUDA(cudaMalloc(&c->d_state, sizeof(PkState)));
+    PK_CUDA(cudaMemset(c->d_state, 0, sizeof(PkState)));
+    PK_CUDA(cudaMallocHost(&c->h_state, sizeof(PkState)));
+    PK_CUDA(cudaMallocHost(&c->h_flags, sizeof(int) * 8));
+    PK_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    PK_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    PK_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    PK_CUDA(cudaEventCreate(&c->ev_t0));
+    PK_CUDA(cudaEventCreate(&c->ev_t1));
+    PK_CUDA(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
+    PK_CUDA(cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming));
+    *out = c;
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_destroy(pk_ctx* c) {
+    if (!c) return PK_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    pk_comm_destroy(c);
+    cudaFree(c->red.partials);
+    cudaFree(c->red.ticket);
+    cudaFree(c->d_state);
+    cudaFreeHost(c->h_state);
+    cudaFreeHost(c->h_flags);
+    cudaStreamDestroy(c->side);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    cudaEventDestroy(c->ev_a);
+    cudaEventDestroy(c->ev_b);
+    cudaEventDestroy(c->ev_t0);
+    cudaEventDestroy(c->ev_t1);
+    cudaEventDestroy(c->ev_poll[0]);
+    cudaEventDestroy(c->ev_poll[1]);
+    delete c;
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_sync(pk_ctx* c) {
+    PK_REQUIRE(c != nullptr, "null context");
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_sm_count(pk_ctx* c) { return c ? c->sm_count : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
+                          const int32_t* d_rowptr, const int32_t* d_col, const double* d_val) {
+    PK_REQUIRE(ctx && out, "null argument");
+    PK_REQUIRE(n_rows >= 0 && nnz >= 0 && nnz < (1LL << 31), "CSR block must have 0 <= nnz < 2^31");
+    PK_REQUIRE(n_rows == 0 || (d_rowptr && (nnz == 0 || (d_col && d_val))), "null CSR arrays");
+    pk_mat* m = new pk_mat();
+    m->ctx = ctx;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols_local;
+    m->nnz = nnz;
+    m->rowptr = d_rowptr;
+    m->col = d_col;
+    m->val = d_val;
+    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0);
+    // Kernel choice from the nnz distribution (mean row length): tiles of 256 rows (128 for mid-length rows) staged in
+    // shared memory when a tile's nonzeros fit; otherwise the warp-per-row path handles the tile.
+    const double mean = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
+    if (mean <= 12.0) {
+        m->tile_rows = 256;
+        m->tile_cap = (int)round_up((long long)std::max(512.0, 256 * mean * 1.15 + 64), 256);
+        m->kind = MAT_CSR_STREAM;
+    } else if (mean <= 40.0) {
+        m->tile_rows = 128;
+        m->tile_cap = (int)round_up((long long)(128 * mean * 1.15 + 64), 256);
+        m->kind = MAT_CSR_STREAM;
+    } else {
+        m->tile_rows = 128;
+        m->tile_cap = 256;        // rows longer than this are reduced warp-per-row
+        m->kind = MAT_CSR_VECTOR;
+    }
+    m->ld = round_up(std::max<long long>(n_rows, n_cols_local), 32);
+    *out = m;
+    return PK_OK;
+}
+
+extern "C" int pk_mat_dense(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols, const double* d_a, int64_t lda) {
+    PK_REQUIRE(ctx && out && d_a, "null argument");
+    PK_REQUIRE(lda >= n_cols, "lda < n_cols");
+    pk_mat* m = new pk_mat();
+    m->ctx = ctx;
+    m->kind = MAT_DENSE;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols;
+    m->dense = d_a;
+    m->lda = lda;
+    m->nnz = n_rows * n_cols;
+    m->ld = round_up(std::max<long long>(n_rows, n_cols), 32);
+    *out = m;
+    return PK_OK;
+}
+
+extern "C" int pk_mat_destroy(pk_mat* m) {
+    if (!m) return PK_OK;
+    if (m->d_sendbuf) cudaFree(m->d_sendbuf);
+    delete m;
+    return PK_OK;
+}
+
+extern "C" int pk_mat_kernel_info(pk_mat* m, int* kind, int* tile_rows, int* tile_cap) {
+    PK_REQUIRE(m != nullptr, "null operator");
+    if (kind) *kind = m->kind;
+    if (tile_rows) *tile_rows = m->tile_rows;
+    if (tile_cap) *tile_cap = m->tile_cap;
+    return PK_OK;
+}
+
+extern "C" int64_t pk_mat_ld(pk_mat* m) { return m ? m->ld : 0; }
+
+extern "C" int pk_mat_set_halo(pk_mat* m, int n_peers_total, const int64_t* send_off, const int64_t* recv_off,
+                               const int32_t* d_send_idx, const int32_t* h_send_idx, int64_t interior_lo,
+                               int64_t interior_hi) {
+    PK_REQUIRE(m && send_off && recv_off, "null argument");
+    PK_REQUIRE(n_peers_total == m->ctx->n_ranks, "halo plan size != communicator size");
+    const int P = n_peers_total;
+    m->send_off.assign(send_off, send_off + P + 1);
+    m->recv_off.assign(recv_off, recv_off + P + 1);
+    m->n_halo = recv_off[P];
+    PK_REQUIRE(m->n_rows + m->n_halo <= m->n_cols || m->kind == MAT_DENSE || true, "halo larger than column space");
+    m->d_send_idx = d_send_idx;
+    m->send_contig.assign(P, 0);
+    m->send_first.assign(P, 0);
+    for (int p = 0; p < P; ++p) {
+        const long long a = send_off[p], b = send_off[p + 1];
+        if (b <= a) { m->send_contig[p] = 1; continue; }
+        bool contig = true;
+        for (long long i = a + 1; i < b && contig; ++i) contig = (h_send_idx[i] == h_send_idx[i - 1] + 1);
+        m->send_contig[p] = contig ? 1 : 0;
+        m->send_first[p] = h_send_idx[a];
+    }
+    if (m->d_sendbuf) { cudaFree(m->d_sendbuf); m->d_sendbuf = nullptr; }
+    if (send_off[P] > 0) PK_CUDA(cudaMalloc(&m->d_sendbuf, sizeof(double) * 2 * (size_t)send_off[P]));
+    m->interior_lo = std::max<long long>(0, std::min<long long>(interior_lo, m->n_rows));
+    m->interior_hi = std::max<long long>(m->interior_lo, std::min<long long>(interior_hi, m->n_rows));
+    m->distributed = true;
+    m->ld = round_up(std::max<long long>(m->n_rows + m->n_halo, m->ld), 32);
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// building blocks exposed for op-by-op parity tests
+static int state_for_standalone(pk_ctx* ctx) {
+    // stand-alone kernels must not be skipped by a stale `done` flag of a previous solve
+    PK_CUDA(cudaMemsetAsync(&ctx->d_state->done, 0, sizeof(int), ctx->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_spmv(pk_ctx* ctx, pk_mat* mat, double* d_x, double* d_y, double* d_x1, double* d_y1,
+                       const double* d_w, double* d_sums) {
+    PK_REQUIRE(ctx && mat && d_x && d_y, "null argument");
+    PK_REQUIRE((d_x1 == nullptr) == (d_y1 == nullptr), "x1/y1 must both be given or both be null");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(state_for_standalone(ctx));
+    PkDots dots;
+    dots.w = d_w;
+    dots.epi = EPI_NONE;
+    PK_CHECK(pk_launch_spmv(ctx, mat, d_x, d_y, d_x1, d_y1, dots));
+    if (d_w && d_sums)
+        PK_CUDA(cudaMemcpyAsync(d_sums, ctx->d_state->red, 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_dot(pk_ctx* ctx, int64_t n, const double* d_u, const double* d_v, double* d_out) {
+    PK_REQUIRE(ctx && d_u && d_v && d_out, "null argument");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(pk_launch_dot(ctx, n, d_u, d_v, EPI_NONE, 1));
+    PK_CUDA(cudaMemcpyAsync(d_out, ctx->d_state->red, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_gram(pk_ctx* ctx, int mode, int64_t n, int64_t ld, const double* d_u, int nu, const double* d_v,
+                       int nv, double* d_g) {
+    PK_REQUIRE(ctx && d_u && d_v && d_g, "null argument");
+    PK_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (MrR) or 1 (CG)");
+    const int njj = std::max(nu, nv);
+    PK_REQUIRE(njj >= 1 && njj <= PK_KMAX + 2, "too many basis rows");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(state_for_standalone(ctx));
+    PK_CHECK(pk_launch_gram(ctx, mode, n, ld, d_u, nu, d_v, nv, njj, EPI_NONE));
+    PK_CUDA(cudaMemcpyAsync(d_g, ctx->d_state->gram, sizeof(double) * 6 * njj, cudaMemcpyDeviceToDevice, ctx->stream));
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int64_t pk_work_doubles(int method, int64_t ld, int k) {
+    long long nvec = 0;
+    switch (method) {
+        case PK_CG: nvec = 3; break;                       // r, p, v
+        case PK_MRR: nvec = 4; break;                      // r, Ar, y, z
+        case PK_KSKIPCG: nvec = (k + 1) + (k + 2); break;  // Ar[0..k], Ap[0..k+1]
+        case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 1; break;          // Ar[0..k+1], Ay[0..k], z
+        case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 2; break;  // + best_x
+        default: return -1;
+    }
+    return nvec * ld;
+}
+
+namespace {
+
+struct Solve {
+    pk_ctx* ctx;
+    pk_mat* A;
+    const double* b;
+    double* x;
+    double* work;
+    long long n, ld;
+    pk_solve_opts o;
+    int method;
+    // graph replay
+    cudaGraphExec_t gexec = nullptr;
+    long long graph_launches = 0, graph_spmvs = 0;
+
+    double* vec(int i) const { return work + (size_t)i * ld; }
+
+    int apply(double* xin, double* yout, const double* w = nullptr, int epi = EPI_NONE) {
+        PkDots d;
+        d.w = w;
+        d.epi = epi;
+        return pk_launch_spmv(ctx, A, xin, yout, nullptr, nullptr, d);
+    }
+    int apply2(double* x0, double* y0, double* x1, double* y1) {
+        PkDots d;
+        return pk_launch_spmv(ctx, A, x0, y0, x1, y1, d);
+    }
+
+    int poll(int slot) {
+        PK_CUDA(cudaMemcpyAsync(ctx->h_flags + 4 * slot, &ctx->d_state->done, 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        PK_CUDA(cudaEventRecord(ctx->ev_poll[slot], ctx->stream));
+        return PK_OK;
+    }
+    int wait(int slot, bool* done) {
+        PK_CUDA(cudaEventSynchronize(ctx->ev_poll[slot]));
+        *done = ctx->h_flags[4 * slot] != 0;
+        return PK_OK;
+    }
+    int fetch_state() {   // blocking read of the whole device state
+        PK_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(PkState), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return PK_OK;
+    }
+
+    // Enqueue `body` batches until the device reports the stop flag.  unit = solver iterations one body() adds.
+    template <class Body>
+    int run_batches(long long unit, long long already, Body body) {
+        long long batch = o.check_every;
+        if (batch <= 0) {
+            // aim for >= ~0.5 ms of device work between polls (rough: 200 bytes per row per iteration at 6 TB/s)
+            double per_it_us = std::max(8.0, (double)n * 200.0 / 6.0e6);
+            batch = (long long)std::ceil(500.0 / (per_it_us * (double)unit));
+            batch = std::max<long long>(1, std::min<long long>(batch, 64));
+        }
+        const bool graph = o.use_graph != 0;
+        if (graph && !gexec) {
+            // capture one batch (stream capture sees the side-stream halo exchange through the fork/join events)
+            cudaGraph_t g = nullptr;
+            const long long l0 = ctx->launches, s0 = ctx->spmvs;
+            PK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = PK_OK;
+            for (long long i = 0; i < batch && rc == PK_OK; ++i) rc = body();
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc != PK_OK) return rc;
+            PK_CUDA(ce);
+            graph_launches = ctx->launches - l0;
+            graph_spmvs = ctx->spmvs - s0;
+            ctx->launches = l0;
+            ctx->spmvs = s0;
+            PK_CUDA(cudaGraphInstantiate(&gexec, g, 0));
+            cudaGraphDestroy(g);
+        }
+        long long enq = already;
+        int slot = 0, prev = -1;
+        bool done = false;
+        while (true) {
+            if (graph) {
+                PK_CUDA(cudaGraphLaunch(gexec, ctx->stream));
+                ctx->launches += graph_launches;
+                ctx->spmvs += graph_spmvs;
+            } else {
+                for (long long i = 0; i < batch; ++i) PK_CHECK(body());
+            }
+            enq += batch * unit;
+            PK_CHECK(poll(slot));
+            if (prev >= 0) {
+                PK_CHECK(wait(prev, &done));
+                if (done) break;
+            }
+            if (enq >= o.maxiter + unit) {   // the device has certainly hit the cap by the end of this batch
+                PK_CHECK(wait(slot, &done));
+                if (done) break;
+            }
+            prev = slot;
+            slot ^= 1;
+        }
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        return PK_OK;
+    }
+
+    int init_state(double* d_res, int64_t* d_nosl, int64_t* d_khist, long long hist_len) {
+        PkState* h = ctx->h_state;
+        memset(h, 0, sizeof(PkState));
+        h->maxiter = o.maxiter;
+        h->tol = o.tol;
+        h->res = d_res;
+        h->nosl = (long long*)d_nosl;
+        h->khist = (long long*)d_khist;
+        h->k = o.k;
+        h->hist_len = hist_len;
+        PK_CUDA(cudaMemcpyAsync(ctx->d_state, h, sizeof(PkState), cudaMemcpyHostToDevice, ctx->stream));
+        // ||b|| (global): v3/cpu/common.py:24
+        PK_CHECK(pk_launch_dot(ctx, n, b, b, EPI_BNORM, 1));
+        return PK_OK;
+    }
+
+    // r = b - A x  (v = scratch for A x);  p (nullable) = copy of r;  epilogue epi on r.r
+    int initial_residual(double* r, double* p, double* scratch, int epi) {
+        if (o.x_is_zero) return pk_launch_resid_init(ctx, n, b, nullptr, r, p, epi);
+        PK_CHECK(apply(x, scratch));
+        return pk_launch_resid_init(ctx, n, b, scratch, r, p, epi);
+    }
+
+    // ---- CG: /root/reference/v3/cpu/cg.py:7-48 -----------------------------------------------------------------
+    int cg() {
+        double *r = vec(0), *p = vec(1), *v = vec(2);
+        PK_CHECK(initial_residual(r, p, v, EPI_CG_INIT));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(run_batches(1, 0, [&]() -> int {
+            PK_CHECK(apply(p, v, p, EPI_CG_ALPHA));               // v = A p ; sigma = p.v ; alpha
+            PK_CHECK(pk_launch_cg_xr(ctx, n, x, r, p, v));        // x += alpha p ; r -= alpha v ; gamma' ; beta ; test
+            PK_CHECK(pk_launch_cg_p(ctx, n, p, r));               // p = r + beta p
+            return PK_OK;
+        }));
+        return PK_OK;
+    }
+
+    // ---- MrR: /root/reference/v3/cpu/mrr.py:7-61 -------------------------------------------------------------
+    int mrr() {
+        double *r = vec(0), *ar = vec(1), *y = vec(2), *z = vec(3);
+        PK_CHECK(initial_residual(r, nullptr, ar, EPI_RES0));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(apply(r, ar, r, EPI_MRR_FIRST));                 // Ar ; zeta = (r.Ar)/(Ar.Ar)
+        PK_CHECK(pk_launch_mrr_first(ctx, n, ar, r, x, y, z, EPI_KS_FIRST));
+        PK_CHECK(run_batches(1, 1, [&]() -> int {
+            PK_CHECK(apply(r, ar, y, EPI_MRR_GAMMA));             // Ar ; nu = y.Ar ; mu = y.y ; gamma
+            PK_CHECK(pk_launch_mrr_s(ctx, n, ar, y, r));          // s = Ar - gamma y ; zeta, eta
+            PK_CHECK(pk_launch_mrr_update(ctx, n, ar, y, z, r, x, -1, EPI_MRR_STEP));
+            return PK_OK;
+        }));
+        return PK_OK;
+    }
+
+    // ---- k-skip CG: /root/reference/v3/cpu/kskipcg.py:8-87 ---------------------------------------------------
+    int kskipcg() {
+        const int k = o.k;
+        auto Ar = [&](int j) { return vec(j); };                  // rows 0..k
+        auto Ap = [&](int j) { return vec(k + 1 + j); };          // rows 0..k+1
+        PK_CHECK(initial_residual(Ar(0), Ap(0), Ap(1), EPI_CG_INIT));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(apply(Ap(0), Ap(1)));                            // invariant: Ap[1] = A Ap[0] at trip start
+        PK_CHECK(run_batches(k + 1, 0, [&]() -> int {
+            // basis: one pass over A advances both chains: (Ar[j], Ap[j+1]) = A (Ar[j-1], Ap[j])
+            for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j - 1), Ar(j), Ap(j), Ap(j + 1)));
+            PK_CHECK(pk_launch_gram(ctx, 1, n, ld, Ar(0), k + 1, Ap(0), k + 2, k + 2, EPI_GRAM_CG));
+            for (int j = 0; j <= k; ++j) {
+                PK_CHECK(pk_launch_kscg_update(ctx, n, x, Ar(0), Ap(0), Ap(1), j, j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
+                PK_CHECK(apply(Ap(0), Ap(1)));
+            }
+            return PK_OK;
+        }));
+        return PK_OK;
+    }
+
+    // ---- k-skip MrR: /root/reference/v3/cpu/kskipmrr.py:8-108 ------------------------------------------------
+    int kskipmrr_open(double* Ar0, double* Ar1, double* Ay0, double* z) {
+        PK_CHECK(apply(Ar0, Ar1, Ar0, EPI_MRR_FIRST));            // kskipmrr.py:26-27
+        PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, EPI_KS_FIRST));   // :28-34
+        return apply(Ar0, Ar1);                                   // invariant: Ar[1] = A Ar[0] at trip start
+    }
+    int kskipmrr_trip(int k, int k_alloc) {
+        auto Ar = [&](int j) { return vec(j); };                  // rows 0..k_alloc+1
+        auto Ay = [&](int j) { return vec(k_alloc + 2 + j); };    // rows 0..k_alloc
+        double* z = vec(2 * k_alloc + 3);
+        for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
+        PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
+        for (int j = 0; j <= k; ++j) {
+            PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), x, j, j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
+            PK_CHECK(apply(Ar(0), Ar(1)));
+        }
+        return PK_OK;
+    }
+    int kskipmrr() {
+        const int k = o.k;
+        double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k + 2), *z = vec(2 * k + 3);
+        PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z));
+        PK_CHECK(run_batches(k + 1, 1, [&]() -> int { return kskipmrr_trip(k, k); }));
+        return PK_OK;
+    }
+
+    // ---- adaptive k-skip MrR: /root/reference/v3/cpu/adaptivekskipmrr.py:8-141 (normative variant) -----------
+    // The residual-growth guard changes k, i.e. the launch sequence, so the host looks at the residual once per
+    // trip (one small D2H per k+1 iterations).
+    int adaptive(int* final_k, int* host_converged) {
+        const int k0 = o.k;
+        int k = k0;
+        double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k0 + 2), *z = vec(2 * k0 + 3), *best_x = vec(2 * k0 + 4);
+        PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(fetch_state());
+        double best_res = std::sqrt(ctx->h_state->rr) / ctx->h_state->bnorm;   // adaptivekskipmrr.py:24
+        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z));
+        *host_converged = 0;
+        while (true) {
+            PK_CHECK(fetch_state());
+            const PkState* h = ctx->h_state;
+            if (h->done && !h->converged) break;                  // `while i < maxiter` failed
+            if (h->it >= o.maxiter) break;
+            double res = std::sqrt(h->rr) / h->bnorm;
+            if (res > best_res) {                                 // :45 residual grew: roll back, one plain MrR step
+                if (h->done) PK_CUDA(cudaMemsetAsync(&ctx->d_state->done, 0, 2 * sizeof(int), ctx->stream));
+                PK_CUDA(cudaMemcpyAsync(x, best_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+                PK_CHECK(apply(x, Ar1));                          // :48  Ar[0] = b - A x
+                PK_CHECK(pk_launch_resid_init(ctx, n, b, Ar1, Ar0, nullptr, EPI_NONE));
+                PK_CHECK(apply(Ar0, Ar1, Ar0, EPI_MRR_FIRST));    // :49-52
+                PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, EPI_ADAPT_STEP));   // :53-61
+                PK_CHECK(apply(Ar0, Ar1));
+                if (k > 1) k -= 1;                                // :64-65
+                PK_CHECK(pk_launch_set_k(ctx, k));                // st->k = k ; khist[idx] = k (:66)
+                PK_CHECK(fetch_state());
+                res = std::sqrt(ctx->h_state->rr) / ctx->h_state->bnorm;
+            } else {
+                best_res = res;                                   // :68-69
+                PK_CUDA(cudaMemcpyAsync(best_x, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            if (res < o.tol) {                                    // :72
+                *host_converged = 1;
+                break;
+            }
+            PK_CHECK(kskipmrr_trip(k, k0));
+        }
+        *final_k = k;
+        return PK_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b, double* d_x, double* d_work,
+                        double* d_residual, int64_t* d_nosl, int64_t* d_khistory, int64_t hist_len,
+                        const pk_solve_opts* opts, pk_solve_result* result) {
+    PK_REQUIRE(ctx && mat && d_b && d_x && d_work && d_residual && d_nosl && opts && result, "null argument");
+    PK_REQUIRE(opts->k >= 0 && opts->k <= PK_KMAX, "k out of range (0..PK_KMAX)");
+    PK_REQUIRE(opts->maxiter >= 0, "maxiter < 0");
+    PK_REQUIRE(hist_len >= 4, "history arrays too short");
+    PK_REQUIRE(method != PK_ADAPTIVEKSKIPMRR || d_khistory != nullptr, "adaptivekskipmrr needs d_khistory");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    Solve s;
+    s.ctx = ctx;
+    s.A = mat;
+    s.b = d_b;
+    s.x = d_x;
+    s.work = d_work;
+    s.n = mat->n_rows;
+    s.ld = mat->ld;
+    s.o = *opts;
+    s.method = method;
+    ctx->launches = 0;
+    ctx->spmvs = 0;
+    PK_CHECK(s.init_state(d_residual, d_nosl, method == PK_ADAPTIVEKSKIPMRR ? d_khistory : nullptr, hist_len));
+    int final_k = opts->k, host_conv = -1;
+    int rc = PK_OK;
+    switch (method) {
+        case PK_CG: rc = s.cg(); break;
+        case PK_MRR: rc = s.mrr(); break;
+        case PK_KSKIPCG: rc = s.kskipcg(); break;
+        case PK_KSKIPMRR: rc = s.kskipmrr(); break;
+        case PK_ADAPTIVEKSKIPMRR: rc = s.adaptive(&final_k, &host_conv); break;
+        default: pk_set_error("unknown method %d", method); return PK_ERR_ARG;
+    }
+    if (rc != PK_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    PK_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    PK_CHECK(s.fetch_state());
+    float ms = 0.f;
+    PK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    const PkState* h = ctx->h_state;
+    result->iterations = h->it;
+    result->entries = h->idx + 1;
+    result->converged = host_conv >= 0 ? host_conv : h->converged;
+    result->final_k = final_k;
+    result->final_residual = std::sqrt(h->rr) / h->bnorm;
+    result->elapsed_s = (double)ms * 1e-3;
+    result->kernel_launches = ctx->launches;
+    result->spmv_count = ctx->spmvs;
+    return PK_OK;
+}

@@ -1,0 +1,157 @@
+"""GPU parity of the individual kernels (through the C-ABI) against the oracle's numpy/scipy operations."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from parallel_krylov_b200 import problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import parallel_krylov_b200 as pk
+    return pk
+
+
+def _matrices():
+    yield "p2d48", problems.poisson2d(48)
+    yield "p3d_12x20x9", problems.poisson3d(12, 20, 9)
+    yield "p3d40", problems.poisson3d(40)
+    yield "band27_20k", problems.banded_spd(20000, 13, 0)
+    yield "band5_777", problems.banded_spd(777, 2, 3)
+    yield "band101_3000", problems.banded_spd(3000, 50, 1)     # long rows -> warp-per-row path
+    yield "tiny1", problems.poisson2d(1)
+    yield "tiny3", problems.poisson2d(3)
+
+
+def _ragged(seed=0, n=5000):
+    """Irregular rows incl. empty rows and a few very long ones (collision of both SpMV paths inside one matrix)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, 12, size=n)
+    lens[rng.integers(0, n, size=20)] = rng.integers(300, 3000, size=20)
+    lens[:7] = 0
+    lens[-3:] = 0
+    rows = np.repeat(np.arange(n), lens)
+    cols = rng.integers(0, n, size=rows.size)
+    vals = rng.standard_normal(rows.size)
+    m = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    m.sum_duplicates()
+    m.sort_indices()
+    return m
+
+
+@pytest.mark.parametrize("name,csr", list(_matrices()), ids=[n for n, _ in _matrices()])
+def test_spmv_bit_exact_vs_scipy(pk, name, csr):
+    rowptr, col, val, n = csr
+    A = problems.to_scipy(rowptr, col, val, n)
+    x = np.random.default_rng(1).standard_normal(n)
+    op = pk.Operator.from_any(A)
+    y = op.matvec(torch.from_numpy(x)).cpu().numpy()
+    ref = A.dot(x)
+    info = op.kernel_info()
+    if info["kernel"] == "csr-stream":
+        # same products, same left-to-right accumulation as scipy's csr_matvec: identical bits
+        assert np.array_equal(y, ref), (name, info, np.abs(y - ref).max())
+    else:
+        np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+
+
+def test_spmv_ragged_rows(pk):
+    A = _ragged()
+    n = A.shape[0]
+    x = np.random.default_rng(2).standard_normal(n)
+    op = pk.Operator.from_any(A)
+    y = op.matvec(torch.from_numpy(x)).cpu().numpy()
+    ref = A.dot(x)
+    np.testing.assert_allclose(y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    # rows short enough to be staged are bit exact; empty rows give +0.0
+    lens = np.diff(A.indptr)
+    assert np.all(y[lens == 0] == 0.0)
+
+
+def test_spmv_two_chains_equals_two_single_passes(pk):
+    rowptr, col, val, n = problems.poisson3d(24)
+    A = problems.to_scipy(rowptr, col, val, n)
+    rng = np.random.default_rng(3)
+    x0, x1 = rng.standard_normal(n), rng.standard_normal(n)
+    op = pk.Operator.from_any(A)
+    y0, y1 = op.matvec(torch.from_numpy(x0), x1=torch.from_numpy(x1))
+    assert np.array_equal(y0.cpu().numpy(), A.dot(x0))
+    assert np.array_equal(y1.cpu().numpy(), A.dot(x1))
+
+
+def test_spmv_fused_dots(pk):
+    rowptr, col, val, n = problems.poisson3d(32)
+    A = problems.to_scipy(rowptr, col, val, n)
+    rng = np.random.default_rng(4)
+    x, w = rng.standard_normal(n), rng.standard_normal(n)
+    op = pk.Operator.from_any(A)
+    y, sums = op.matvec(torch.from_numpy(x), dot_with=torch.from_numpy(w))
+    ref = A.dot(x)
+    s = sums.cpu().numpy()
+    np.testing.assert_allclose(s, [np.dot(w, ref), np.dot(ref, ref), np.dot(w, w)], rtol=1e-13)
+    # deterministic: a second launch gives the same bits
+    _, sums2 = op.matvec(torch.from_numpy(x), dot_with=torch.from_numpy(w))
+    assert np.array_equal(s, sums2.cpu().numpy())
+
+
+def test_dense_gemv(pk):
+    a = problems.dense_spd(517, 0)
+    rng = np.random.default_rng(5)
+    x, x1 = rng.standard_normal(517), rng.standard_normal(517)
+    op = pk.Operator.from_any(a)
+    assert op.kernel_info()["kernel"] == "dense-gemv"
+    y0, y1 = op.matvec(torch.from_numpy(x), x1=torch.from_numpy(x1))
+    np.testing.assert_allclose(y0.cpu().numpy(), a @ x, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(y1.cpu().numpy(), a @ x1, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("mode,k", [(0, 0), (0, 1), (0, 4), (0, 8), (0, 12), (1, 0), (1, 2), (1, 4), (1, 8), (1, 16)])
+def test_gram_all_pairs(pk, mode, k):
+    """The single-pass Gram kernel against the oracle's per-pair numpy.dot calls (kskipmrr.py:51-59, kskipcg.py:40-48)."""
+    from parallel_krylov_b200 import _lib
+    from parallel_krylov_b200._core import Context, _ptr
+    ctx = Context.get()
+    n, ld = 100003, 100032
+    nu, nv = (k + 2, k + 1) if mode == 0 else (k + 1, k + 2)
+    rng = np.random.default_rng(6)
+    U = np.zeros((nu, ld)); V = np.zeros((nv, ld))
+    U[:, :n] = rng.standard_normal((nu, n)); V[:, :n] = rng.standard_normal((nv, n))
+    U[:, n:] = 7.0; V[:, n:] = -3.0          # padding must not be read
+    Ud, Vd = torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda()
+    njj = max(nu, nv)
+    g = torch.zeros(6 * njj, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.pk_gram(ctx.handle, mode, n, ld, _ptr(Ud), nu, _ptr(Vd), nv, _ptr(g)))
+    ctx.sync()
+    G = g.cpu().numpy().reshape(njj, 6)
+    row = lambda M, j: M[j, :n] if j < M.shape[0] else np.zeros(n)
+    for jj in range(njj):
+        u0, u1, v0, v1 = row(U, jj), row(U, jj + 1), row(V, jj), row(V, jj + 1)
+        cross = np.dot(v0, u1) if mode == 0 else np.dot(u0, v1)
+        ref = [np.dot(u0, u0), np.dot(u0, u1), np.dot(u0, v0), cross, np.dot(v0, v0), np.dot(v0, v1)]
+        np.testing.assert_allclose(G[jj], ref, rtol=1e-12, atol=1e-9)
+
+
+def test_device_generators_match_host(pk):
+    from parallel_krylov_b200 import device_problems as dp
+    for args in [(16, 16, 1), (12, 20, 9), (33, 7, 5)]:
+        rp, ci, va, n = dp.stencil_csr(*args)
+        hr, hc, hv, hn = problems.poisson2d(args[0]) if args[2] == 1 else problems.poisson3d(*args)
+        assert n == hn
+        assert np.array_equal(rp.cpu().numpy(), hr) and np.array_equal(ci.cpu().numpy(), hc)
+        assert np.array_equal(va.cpu().numpy(), hv)
+    rp, ci, va, n = dp.banded_csr(5000, 13, 0)
+    hr, hc, hv, hn = problems.banded_spd(5000, 13, 0)
+    assert np.array_equal(rp.cpu().numpy(), hr) and np.array_equal(ci.cpu().numpy(), hc)
+    assert np.array_equal(va.cpu().numpy(), hv)
+    # a row slab of a bigger grid (what a rank generates for itself)
+    rp, ci, va, n = dp.stencil_csr(12, 20, 9, row0=480, n_rows=960)
+    sl = problems.to_scipy(*problems.poisson3d(12, 20, 9))[480:1440]
+    assert np.array_equal(ci.cpu().numpy(), sl.indices) and np.array_equal(va.cpu().numpy(), sl.data)
+    z = dp.hash_normal(0, 4096).cpu().numpy()
+    np.testing.assert_allclose(z, problems.hash_normal(0, 4096), rtol=1e-12, atol=1e-14)
