@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py — solver iterations/s of the parallel-krylov hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Headline workload (all N, strong scaling): CG on the 3-D 7-point Poisson system 512^3 (n = 134 217 728,
+nnz = 937 951 232), fp64, x0 = 0, tol = 1e-8, one *step* = one call of the public solver with an iteration cap of
+300 (BASELINE.json: "CG iters/s & achieved HBM GB/s, 3D Poisson fp64 at 1/2/4/8 B200"; the north-star scaling target
+is quoted on 512^3).  Inputs are far larger than L2 (11.8 GB of CSR + 1 GiB vectors), so no L2 flush is needed.
+
+ONE JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("PK_QUIET", "1")
+
+import numpy as np  # noqa: E402
+
+# name -> (solver, k, matrix kind, dims, iteration cap per step)
+WORKLOADS = {
+    "cg_p3d512": ("cg", None, "stencil", (512, 512, 512), 300),
+    "cg_p3d256": ("cg", None, "stencil", (256, 256, 256), 500),
+    "cg_p3d128": ("cg", None, "stencil", (128, 128, 128), 500),
+    "cg_p2d256": ("cg", None, "stencil", (256, 256, 1), 763),
+    "mrr_p3d128": ("mrr", None, "stencil", (128, 128, 128), 500),
+    "mrr_p3d256": ("mrr", None, "stencil", (256, 256, 256), 500),
+    "kskipcg4_p3d256": ("kskipcg", 4, "stencil", (256, 256, 256), 500),
+    "kskipmrr8_p3d256": ("kskipmrr", 8, "stencil", (256, 256, 256), 495),
+    "kskipmrr4_p3d256": ("kskipmrr", 4, "stencil", (256, 256, 256), 500),
+    "kskipmrr8_band32m": ("kskipmrr", 8, "banded", (1 << 25, 13), 46),
+    "cg_band32m": ("cg", None, "banded", (1 << 25, 13), 42),
+    "adaptive8_p3d512": ("adaptivekskipmrr", 8, "stencil", (512, 512, 512), 297),
+}
+DEFAULT_WORKLOAD = "cg_p3d512"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def algorithmic_bytes(solver, k, n, nnz):
+    """minimal-traffic model, per solver iteration (and for one operator application)."""
+    b_spmv = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
+    if solver == "cg":
+        per_it = b_spmv + 72.0 * n
+    elif solver == "mrr":
+        per_it = b_spmv + 104.0 * n          # literal form: y read for the phase-1 dots, s-phase re-read, 5R/4W update
+    elif solver == "kskipcg":
+        per_it = ((3 * k + 2) * b_spmv + 8.0 * n * (2 * k + 3) + 56.0 * n * (k + 1)) / (k + 1)
+    else:
+        per_it = ((3 * k + 2) * b_spmv + 8.0 * n * (2 * k + 3) + 72.0 * n * (k + 1)) / (k + 1)
+    return b_spmv, per_it
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, timed on this box's host cores.
+    The reference is pure Python (numpy/scipy), so there is no oracle/_ref binary: this runs the oracle PORT
+    (oracle/krylov_oracle.py — bit-identical to /root/reference/v3/cpu on the golden vectors), scipy's serial
+    csr_matvec + OpenBLAS-threaded dots, i.e. all the host threads the reference itself can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import krylov_oracle as oracle
+    import host_kernels as hk
+    from parallel_krylov_b200 import problems
+    solver, k, kind, dims, cap = WORKLOADS[args.workload]
+    t0 = time.time()
+    if kind == "stencil":
+        rowptr, col, val, n = hk.stencil_csr(*dims)
+    else:
+        rowptr, col, val, n = problems.banded_spd(*dims)
+    A = problems.to_scipy(rowptr, col, val, n)
+    b = problems.hash_normal(0, n)
+    log(f"[reference] built {args.workload} on host in {time.time() - t0:.1f}s (n={n}, nnz={len(val)})")
+    # bounded sample: a few iterations per step so the whole run stays within minutes
+    kk = (k or 0) + 1
+    probe_it = kk + (1 if solver != "cg" and solver != "kskipcg" else 0)
+    kw = {"k": k} if k is not None else {}
+    t1 = time.perf_counter()
+    _, info = oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=probe_it, **kw)
+    per_it = max(info["time"] / max(int(info["nosl"][-1]), 1), 1e-9)
+    total_steps = args.steps + args.warmup
+    budget_s = 150.0
+    it_per_step = int(max(kk, min(cap, budget_s / total_steps / per_it)))
+    it_per_step = max(kk, (it_per_step // kk) * kk)
+    log(f"[reference] probe: {per_it:.3f} s/iteration -> {it_per_step} iterations per step")
+    for _ in range(args.warmup):
+        oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
+    its, secs = 0, 0.0
+    for _ in range(args.steps):
+        _, info = oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
+        its += int(info["nosl"][-1])
+        secs += info["time"]
+    value = its / secs
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = os.cpu_count()
+    sample = (f"{it_per_step} iterations per step of the same system (x0=0), timed like the reference "
+              f"(perf_counter around the loop, after the initial residual)")
+    line = {
+        "impl": "reference", "metric": "solver_iterations_per_s", "value": value, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, n, len(val), it_per_step),
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": int(blas_threads), "kind": "port",
+                         "sample": sample, "host_cpus": os.cpu_count(),
+                         "note": "scipy csr_matvec is serial; numpy dots use OpenBLAS threads"},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(name, n, nnz, cap):
+    solver, k, kind, dims, _ = WORKLOADS[name]
+    desc = {"stencil": f"{'3-D 7-point' if dims[2] > 1 else '2-D 5-point'} Poisson {'x'.join(map(str, dims))}",
+            "banded": f"banded SPD, {2 * dims[1] + 1} diagonals" if kind == "banded" else ""}[kind]
+    return {"workload": f"{solver}{'' if k is None else ' k=' + str(k)} on {desc} (n={n}, nnz={nnz}) fp64, "
+                        f"x0=0, tol=1e-8, iteration cap {cap} per step",
+            "name": name, "l2": "inputs >> L2 (no flush needed)" if nnz * 12 > 4e8 else "L2 flushed between steps",
+            "partition": "contiguous block rows, sharded vectors, halo exchange + all-reduced dots"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import parallel_krylov_b200 as pk
+    from parallel_krylov_b200 import device_problems as dp
+    from parallel_krylov_b200 import _lib
+    from parallel_krylov_b200._core import Context, Operator, solve
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context.get(local_rank)
+
+    solver, k, kind, dims, cap = WORKLOADS[args.workload]
+    if args.maxiter:
+        cap = args.maxiter
+    n = int(np.prod(dims)) if kind == "stencil" else dims[0]
+    base = n // world
+    row0 = rank * base
+    n_loc = base if rank < world - 1 else n - row0
+    t0 = time.time()
+    if kind == "stencil":
+        rowptr, colg, val, _ = dp.stencil_csr(*dims, row0=row0, n_rows=n_loc, ctx=ctx)
+    else:
+        rowptr, colg, val, _ = dp.banded_csr(dims[0], dims[1], 0, row0=row0, n_rows=n_loc, ctx=ctx)
+    nnz_loc = int(val.numel())
+    b = dp.hash_normal(0, n_loc, offset=row0, ctx=ctx)
+    if world > 1:
+        from parallel_krylov_b200.mpi import DistOperator
+        offs = [r * base for r in range(world)] + [n]
+        op = DistOperator.from_local_csr(rowptr, colg, val, n, None, ctx, row_offsets=offs)
+        t = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        nnz = int(t.item())
+    else:
+        op = Operator.from_csr_tensors(rowptr, colg, val, n, ctx)
+        nnz = nnz_loc
+    torch.cuda.synchronize()
+    if rank == 0:
+        log(f"[ours] {args.workload}: n={n} nnz={nnz} on {world} GPU(s), generated in HBM in {time.time() - t0:.1f}s; "
+            f"kernel {op.kernel_info()}, halo {op.n_halo}")
+    kw = {"k": k} if k is not None else {}
+
+    def one_solve(graph):
+        return solve(solver, op, b, tol=1e-8, maxiter=cap, use_graph=graph, ctx=ctx, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_solve(False)
+    # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    _lib.check(ctx.lib.pk_prof_begin(ctx.handle, 4096))
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = launches = spmvs = 0
+    loop_s = 0.0
+    for _ in range(args.steps):
+        _, info = one_solve(False)
+        iters += info["iterations"]
+        launches += info["gpu_launches"]
+        spmvs += info["spmv"]
+        loop_s += info["time"]
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = e0.elapsed_time(e1)
+    prof_ms, prof_n = C.c_double(), C.c_int64()
+    _lib.check(ctx.lib.pk_prof_end(ctx.handle, C.byref(prof_ms), C.byref(prof_n)))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = iters / (elapsed_ms * 1e-3)
+
+    # ---- timed region 2: end to end through the public entry point with HOST buffers ---------------------------
+    # (A, b in pinned host memory -> H2D every step, solve, x -> D2H every step)
+    del op
+    h_rowptr = rowptr.cpu().pin_memory()
+    h_col = colg.cpu().pin_memory()
+    h_val = val.cpu().pin_memory()
+    h_b = b.cpu().pin_memory()
+    h_x = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    del rowptr, colg, val
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        if world > 1:
+            from parallel_krylov_b200 import mpi as pkm
+            x, info = getattr(pkm, solver)(None, (h_rowptr, h_col, h_val, n), h_b, tol=1e-8, maxiter=cap,
+                                           gather_x=False, use_graph=False, **kw)
+        else:
+            x, info = getattr(pk, solver)((h_rowptr, h_col, h_val, n), h_b, tol=1e-8, maxiter=cap, use_graph=False, **kw)
+        h_x.copy_(x, non_blocking=False)
+        return info
+
+    e2e_warm = min(args.warmup, 1) if nnz > 2e8 else args.warmup
+    for _ in range(e2e_warm):
+        e2e_step()
+    barrier()
+    e0.record()
+    it2 = 0
+    h2d = 0
+    for _ in range(args.steps):
+        info = e2e_step()
+        it2 += info["iterations"]
+        h2d = info["h2d_bytes"]
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        t = torch.tensor([h2d, n_loc * 8], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        h2d_total, d2h_total = int(t[0].item()), int(t[1].item())
+    else:
+        h2d_total, d2h_total = h2d, n_loc * 8
+    e2e_value = it2 / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (operator application) -------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    b_spmv_loc, _ = algorithmic_bytes(solver, k or 0, n_loc, nnz_loc)      # per launch on this rank
+    _, per_it_bytes = algorithmic_bytes(solver, k or 0, n, nnz)
+    spmv_avg_ms = prof_ms.value / max(prof_n.value, 1)
+    spmv_gbs = b_spmv_loc / (spmv_avg_ms * 1e-3) / 1e9 if spmv_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_spmv_stream (y = A p, fused p.Ap)", "achieved": spmv_gbs, "peak": peak,
+                "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": load_traffic(args.workload),
+                "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_avg_ms,
+                "launches_timed": int(prof_n.value), "peak_source": peak_src,
+                "whole_iteration": {"bytes_per_iteration": per_it_bytes,
+                                    "achieved_gbs": per_it_bytes * value / 1e9 / 1.0,
+                                    "frac_of_peak_x_gpus": per_it_bytes * value / 1e9 / (peak * world)}}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only) -----------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import krylov_oracle as oracle
+        import scipy.sparse as sp
+        A = sp.csr_matrix((h_val.numpy(), h_col.numpy(), h_rowptr.numpy()), shape=(n, n))
+        kk = (k or 0) + 1
+        m = kk * max(1, int(round(3 / kk))) if nnz > 2e8 else kk * max(1, 20 // kk)
+        t_cpu = time.perf_counter()
+        _, ci = oracle.SOLVERS[solver](A, h_b.numpy(), tol=1e-8, maxiter=m, **kw)
+        # extend the sample to ~10-30 s if the first probe was short
+        if ci["time"] < 5.0:
+            m2 = int(min(cap, m * max(2, int(12.0 / max(ci["time"], 1e-3))))) // kk * kk
+            _, ci = oracle.SOLVERS[solver](A, h_b.numpy(), tol=1e-8, maxiter=max(m2, kk), **kw)
+        try:
+            from threadpoolctl import threadpool_info
+            blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        except Exception:
+            blas_threads = os.cpu_count()
+        cpu_its = int(ci["nosl"][-1])
+        cpu_baseline = {"value": cpu_its / ci["time"], "unit": "iterations/s", "cores": int(blas_threads),
+                        "kind": "port", "host_cpus": os.cpu_count(),
+                        "sample": f"{cpu_its} iterations of the same system on the host (oracle/krylov_oracle.py: scipy "
+                                  f"serial csr_matvec + OpenBLAS dots), {ci['time']:.1f}s, timed like the reference"}
+        log(f"[cpu_baseline] {cpu_baseline['value']:.4f} it/s ({time.perf_counter() - t_cpu:.1f}s total)")
+
+    line = {
+        "metric": "solver_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, n, nnz, cap),
+        "iterations_per_step": iters / max(args.steps, 1), "loop_only_iterations_per_s": iters / loop_s,
+        "gpu_launches": int(launches), "spmv_launch_count": int(spmvs),
+        "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_total),
+                "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def load_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/traffic.json), or null when none has been taken for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get("spmv_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--maxiter", type=int, default=0, help="override the per-step iteration cap")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: timing rules ask for >= 3 warm-up steps")
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -53,6 +53,10 @@ int pk_ctx_create(pk_ctx** out, int device, void* stream);
 int pk_ctx_destroy(pk_ctx* ctx);
 int pk_ctx_sync(pk_ctx* ctx);                     /* cudaStreamSynchronize */
 int pk_ctx_sm_count(pk_ctx* ctx);
+/* Per-launch timing of the operator kernel with CUDA event pairs on the context's stream (bench.py's roofline
+ * numerator).  Only plain stream launches are timed (graph replays are not): total over the recorded launches. */
+int pk_prof_begin(pk_ctx* ctx, int max_launches);
+int pk_prof_end(pk_ctx* ctx, double* total_ms, int64_t* n_launches);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* operator (row block of A).  Replaces MultiGpu.alloc() (v3/gpu/common.py:83-109, v3/gpu/mpi/common.py:102-134) */

@@ -21,6 +21,8 @@ solver (the reference's ``kskipcg``/``adaptivekskipmrr`` call ``numpy.dot(A, v)`
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 from numpy import dot
 from numpy.linalg import norm
@@ -38,9 +40,15 @@ class _Log:
         self.maxiter = self.n if maxiter is None else maxiter
         self.res = np.zeros(self.maxiter + 1, F64)
         self.nosl = np.zeros(self.maxiter + 1, np.int64)
+        self.t0 = None
+
+    def start(self):
+        """Where the reference calls start() (e.g. v3/cpu/cg.py:18): after init and the initial residual."""
+        self.t0 = time.perf_counter()
 
     def info(self, last, converged, **extra):
-        out = {"nosl": self.nosl[: last + 1], "residual": self.res[: last + 1], "converged": converged}
+        out = {"nosl": self.nosl[: last + 1], "residual": self.res[: last + 1], "converged": converged,
+               "time": (time.perf_counter() - self.t0) if self.t0 is not None else None}
         out.update(extra)
         return out
 
@@ -53,6 +61,7 @@ def cg(mat, b, x=None, tol=1e-05, maxiter=None):
     p = r.copy()                             # :13
     gamma = dot(r, r)                        # :14
     it, ok = 0, False
+    lg.start()                               # :18
     while it < lg.maxiter:                   # :19
         lg.res[it] = norm(r) / lg.bnorm      # :21
         if lg.res[it] < tol:                 # :22
@@ -88,6 +97,7 @@ def mrr(mat, b, x=None, tol=1e-05, maxiter=None):
     x = lg.x
     r = b - mat.dot(x)                       # mrr.py:12
     lg.res[0] = norm(r) / lg.bnorm           # :13
+    lg.start()                               # :17
     ar, zeta = _mrr_first_step(mat, r)       # :18-19
     y = zeta * ar                            # :20
     z = -zeta * r                            # :21
@@ -153,6 +163,7 @@ def kskipcg(mat, b, x=None, tol=1e-05, maxiter=None, k=0):
     Ar[0] = b - mat.dot(x)                   # :21
     Ap[0] = Ar[0]                            # :22
     it, idx, ok = 0, 0, False
+    lg.start()                               # :27
     while it < lg.maxiter:                   # :28
         lg.res[idx] = norm(Ar[0]) / lg.bnorm  # :30
         if lg.res[idx] < tol:
@@ -242,6 +253,7 @@ def kskipmrr(mat, b, x=None, tol=1e-05, maxiter=None, k=0):
     delta = np.zeros(2 * k + 1, F64)
     Ar[0] = b - mat.dot(x)                   # :21
     lg.res[0] = norm(Ar[0]) / lg.bnorm       # :22
+    lg.start()                               # :25
     Ar[1], zeta = _mrr_first_step(mat, Ar[0])   # :26-27
     Ay[0] = zeta * Ar[1]                     # :28
     z = -zeta * Ar[0]                        # :29
@@ -281,6 +293,7 @@ def adaptivekskipmrr(mat, b, x=None, tol=1e-05, maxiter=None, k=0):
     lg.res[0] = norm(Ar[0]) / lg.bnorm
     best_res = lg.res[0]                     # :24
     best_x = None
+    lg.start()                               # :27
     Ar[1], zeta = _mrr_first_step(mat, Ar[0])   # :28-31
     Ay[0] = zeta * Ar[1]
     z = -zeta * Ar[0]

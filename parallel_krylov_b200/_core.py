@@ -275,7 +275,7 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
     dev = ctx.torch_device
     lib = ctx.lib
     n = op.n_rows
-    if op.n_global != n and op.n_halo == 0 and op.kind != "dense":
+    if op.n_global != n and op.row_offsets is None:
         raise PkError(f"A must be square (got {n} x {op.n_global}); use parallel_krylov_b200.mpi for row blocks")
     ld = op.ld
 

@@ -38,6 +38,8 @@ _SIGS = {
     "pk_ctx_destroy": (C.c_int, [_P]),
     "pk_ctx_sync": (C.c_int, [_P]),
     "pk_ctx_sm_count": (C.c_int, [_P]),
+    "pk_prof_begin": (C.c_int, [_P, C.c_int]),
+    "pk_prof_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pk_mat_csr": (C.c_int, [_P, C.POINTER(_P), _I64, _I64, _I64, _P, _P, _P]),
     "pk_mat_dense": (C.c_int, [_P, C.POINTER(_P), _I64, _I64, _P, _I64]),
     "pk_mat_destroy": (C.c_int, [_P]),

@@ -109,6 +109,10 @@ struct pk_ctx {
     int n_ranks = 1, rank = 0;
     long long launches = 0;          // kernels launched (statistics)
     long long spmvs = 0;
+    // optional per-launch timing of the operator kernel (bench.py's roofline): event pairs around each application
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
 };
 
 enum PkMatKind : int { MAT_CSR_STREAM = 0, MAT_CSR_VECTOR = 1, MAT_DENSE = 2 };

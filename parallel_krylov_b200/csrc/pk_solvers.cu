@@ -84,6 +84,7 @@ extern "C" int pk_ctx_destroy(pk_ctx* c) {
     cudaEventDestroy(c->ev_t1);
     cudaEventDestroy(c->ev_poll[0]);
     cudaEventDestroy(c->ev_poll[1]);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     delete c;
     return PK_OK;
 }
@@ -95,6 +96,36 @@ extern "C" int pk_ctx_sync(pk_ctx* c) {
 }
 
 extern "C" int pk_ctx_sm_count(pk_ctx* c) { return c ? c->sm_count : 0; }
+
+// Per-launch timing of the operator kernel: CUDA event pairs on the launching stream (not under a profiler).
+extern "C" int pk_prof_begin(pk_ctx* c, int max_launches) {
+    PK_REQUIRE(c != nullptr && max_launches > 0, "bad argument");
+    PK_CUDA(cudaSetDevice(c->device));
+    while ((int)c->prof_ev.size() < 2 * max_launches) {
+        cudaEvent_t e;
+        PK_CUDA(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+    }
+    c->prof_used = 0;
+    c->prof_on = true;
+    return PK_OK;
+}
+
+extern "C" int pk_prof_end(pk_ctx* c, double* total_ms, int64_t* n_launches) {
+    PK_REQUIRE(c != nullptr, "null context");
+    PK_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float ms = 0.f;
+        PK_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = (int64_t)(c->prof_used / 2);
+    c->prof_on = false;
+    c->prof_used = 0;
+    return PK_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }

@@ -287,7 +287,25 @@ int launch_gemv(pk_ctx* ctx, pk_mat* m, bool two, const GemvArgs& a, PkRedArgs r
 
 }  // namespace
 
+static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots);
+
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots) {
+    bool prof = false;
+    if (ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size()) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(ctx->stream, &cs);
+        prof = (cs == cudaStreamCaptureStatusNone);
+    }
+    if (prof) PK_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+    int rc = spmv_impl(ctx, m, x, y, x1, y1, dots);
+    if (prof) {
+        PK_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
+    return rc;
+}
+
+static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots) {
     const bool two = (x1 != nullptr);
     PkRedArgs ra;
     ra.partials = ctx->red.partials;

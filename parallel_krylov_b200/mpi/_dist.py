@@ -1,0 +1,286 @@
+"""Row-partitioned multi-GPU layer: one process per GPU, ``torch.distributed`` for the plumbing, NCCL (inside
+libpkrylov) on the data path.
+
+Replaces ``MultiGpu`` of /root/reference/v3/gpu/mpi/common.py:46-171.  The reference keeps every vector replicated on
+every rank and, per mat-vec, broadcasts the full x to each GPU (``memcpyPeer``, :144), gathers the pieces (:156) and
+``comm.Allgather``s the result (:163).  Here vectors are SHARDED like the rows of A, a mat-vec exchanges only the
+entries of x the local block references (the *halo*), and dot products are local partials + one small all-reduce
+(precedent: /root/reference/v1/processes/adaptivekskipmrr.py:104-116).
+
+The halo plan is computed with torch ops on whatever device the index arrays live on, so the same code is exercised
+on CPU tensors over ``gloo`` (tests/test_dist_gloo.py) and on CUDA tensors over ``nccl``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .._core import Context, Operator, _ptr
+from .._lib import PkError, check
+
+
+def _all_gather_int(value: int, group, device) -> list:
+    world = dist.get_world_size(group)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [int(o.item()) for o in out]
+
+
+def _comm_device(group) -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def row_offsets_from_local(n_local: int, group=None) -> list:
+    """Global row offsets [0, n_0, n_0+n_1, ...] of a contiguous block-row partition (the reference's partition,
+    /root/reference/v3/gpu/mpi/common.py:104-131, without its N % P == 0 requirement)."""
+    counts = _all_gather_int(n_local, group, _comm_device(group))
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    return offs
+
+
+def build_halo_plan(rowptr: torch.Tensor, col_global: torch.Tensor, row_offsets: Sequence[int], rank: int,
+                    group=None) -> dict:
+    """From a local CSR block with GLOBAL column indices derive
+      * ``col_local``   — columns renumbered to [owned 0..n_rows) | halo n_rows..n_rows+n_halo),
+      * ``recv_off``    — per peer, which slice of the halo tail it fills (halo sorted by global index ⇒ by owner),
+      * ``send_idx`` / ``send_off`` — per peer, which owned entries this rank must send (local indices),
+      * ``interior``    — the longest run of rows that reference no halo column (overlapped with the exchange).
+    One collective round (sizes) + point-to-point index lists; runs once per operator."""
+    dev = col_global.device
+    world = len(row_offsets) - 1
+    row0, row1 = int(row_offsets[rank]), int(row_offsets[rank + 1])
+    n_rows = row1 - row0
+    colg = col_global.to(torch.int64)
+    ext_mask = (colg < row0) | (colg >= row1)
+    ext_cols = torch.unique(colg[ext_mask])                       # sorted ascending
+    n_halo = int(ext_cols.numel())
+    offs_t = torch.tensor(list(row_offsets), dtype=torch.int64, device=dev)
+    owner = torch.searchsorted(offs_t, ext_cols, right=True) - 1   # ascending because ext_cols is sorted
+    recv_counts = torch.bincount(owner, minlength=world)[:world] if n_halo else torch.zeros(world, dtype=torch.int64, device=dev)
+    recv_off = [0]
+    for c in recv_counts.tolist():
+        recv_off.append(recv_off[-1] + int(c))
+    # renumber columns
+    col_local = colg - row0
+    if n_halo:
+        pos = torch.searchsorted(ext_cols, colg[ext_mask])
+        col_local[ext_mask] = n_rows + pos
+    col_local = col_local.to(torch.int32)
+    # boundary rows -> interior run
+    if n_halo:
+        ext_pos = torch.nonzero(ext_mask, as_tuple=False).flatten()
+        brow = torch.unique(torch.searchsorted(rowptr.to(torch.int64)[1:].contiguous(), ext_pos, right=True))
+        edges = torch.cat([torch.tensor([-1], device=dev, dtype=torch.int64), brow.to(torch.int64),
+                           torch.tensor([n_rows], device=dev, dtype=torch.int64)])
+        gaps = edges[1:] - edges[:-1] - 1
+        g = int(torch.argmax(gaps).item())
+        interior = (int(edges[g].item()) + 1, int(edges[g + 1].item()))
+    else:
+        interior = (0, n_rows)
+
+    # tell every owner which of its entries we need
+    cdev = _comm_device(group) if world > 1 else dev
+    counts_mat = [torch.zeros(world, dtype=torch.int64, device=cdev) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(counts_mat, recv_counts.to(cdev), group=group)
+    else:
+        counts_mat[0] = recv_counts.to(cdev)
+    send_counts = [int(counts_mat[p][rank].item()) for p in range(world)]     # what peer p wants from me
+    send_off = [0]
+    for c in send_counts:
+        send_off.append(send_off[-1] + c)
+    send_idx = torch.zeros(send_off[-1], dtype=torch.int64, device=cdev)
+    if world > 1:
+        ops = []
+        want = ext_cols.to(cdev)
+        for p in range(world):
+            if p == rank:
+                continue
+            if recv_off[p + 1] > recv_off[p]:
+                ops.append(dist.P2POp(dist.isend, want[recv_off[p]:recv_off[p + 1]].contiguous(),
+                                      dist.get_global_rank(group, p) if group is not None else p, group=group))
+            if send_counts[p] > 0:
+                ops.append(dist.P2POp(dist.irecv, send_idx[send_off[p]:send_off[p + 1]],
+                                      dist.get_global_rank(group, p) if group is not None else p, group=group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    send_idx = (send_idx - row0).to(torch.int32)
+    if send_idx.numel() and (int(send_idx.min()) < 0 or int(send_idx.max()) >= n_rows):
+        raise PkError("halo plan: a peer asked for rows this rank does not own")
+    return {"col_local": col_local, "n_halo": n_halo, "recv_off": recv_off, "send_off": send_off,
+            "send_idx": send_idx, "interior": interior, "halo_global": ext_cols, "n_rows": n_rows}
+
+
+class DistOperator(Operator):
+    """A contiguous row block of A on this rank's GPU plus its halo plan."""
+
+    @classmethod
+    def from_local_csr(cls, rowptr: torch.Tensor, col_global: torch.Tensor, val: torch.Tensor, n_global: int,
+                       group=None, ctx: Optional[Context] = None, row_offsets: Optional[Sequence[int]] = None
+                       ) -> "DistOperator":
+        ctx = ctx or Context.get()
+        ctx.init_comm(group)
+        dev = ctx.torch_device
+        rank, world = ctx.rank, ctx.n_ranks
+        h2d = sum(t.numel() * t.element_size() for t in (rowptr, col_global, val) if not t.is_cuda)
+        rowptr = rowptr.to(dev, torch.int32).contiguous()
+        col_global = col_global.to(dev)
+        val = val.to(dev, torch.float64).contiguous()
+        n_rows = rowptr.numel() - 1
+        if row_offsets is None:
+            row_offsets = row_offsets_from_local(n_rows, group) if world > 1 else [0, n_rows]
+        if row_offsets[-1] != n_global:
+            raise PkError(f"row blocks cover {row_offsets[-1]} rows, A has {n_global} columns")
+        plan = build_halo_plan(rowptr, col_global, row_offsets, rank, group)
+        col_local = plan["col_local"].contiguous()
+        del col_global
+        op = cls(ctx)
+        op.tensors = {"rowptr": rowptr, "col": col_local, "val": val}
+        op.n_rows = n_rows
+        op.n_global = int(n_global)
+        op.row0 = int(row_offsets[rank])
+        op.row_offsets = list(row_offsets)
+        op.nnz = int(val.numel())
+        op.kind = "csr"
+        op.n_halo = plan["n_halo"]
+        op.h2d_bytes = h2d
+        op.plan = plan
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_mat_csr(ctx.handle, C.byref(op.handle), n_rows, n_rows + op.n_halo, op.nnz,
+                                     _ptr(rowptr), _ptr(col_local), _ptr(val)), "pk_mat_csr")
+            if world > 1:
+                send_idx_d = plan["send_idx"].to(dev).contiguous()
+                send_idx_h = plan["send_idx"].cpu().contiguous()
+                op.tensors["send_idx"] = send_idx_d
+                so = np.asarray(plan["send_off"], dtype=np.int64)
+                ro = np.asarray(plan["recv_off"], dtype=np.int64)
+                check(ctx.lib.pk_mat_set_halo(op.handle, world, so.ctypes.data_as(C.c_void_p),
+                                              ro.ctypes.data_as(C.c_void_p), _ptr(send_idx_d),
+                                              C.c_void_p(send_idx_h.data_ptr()), plan["interior"][0],
+                                              plan["interior"][1]), "pk_mat_set_halo")
+        return op
+
+    @classmethod
+    def from_local_dense(cls, local_a: torch.Tensor, group=None, ctx: Optional[Context] = None) -> "DistOperator":
+        """Dense row block (local_N x N), the reference's ndarray branch (v3/gpu/mpi/common.py:124-125).  Every column
+        is referenced, so the halo is the whole rest of x: columns are permuted to [owned | others]."""
+        ctx = ctx or Context.get()
+        ctx.init_comm(group)
+        dev = ctx.torch_device
+        rank, world = ctx.rank, ctx.n_ranks
+        h2d = 0 if local_a.is_cuda else local_a.numel() * 8
+        a = local_a.to(dev, torch.float64)
+        n_rows, n_global = int(a.shape[0]), int(a.shape[1])
+        row_offsets = row_offsets_from_local(n_rows, group) if world > 1 else [0, n_rows]
+        row0, row1 = row_offsets[rank], row_offsets[rank + 1]
+        perm = torch.cat([torch.arange(row0, row1, device=dev), torch.arange(0, row0, device=dev),
+                          torch.arange(row1, n_global, device=dev)])
+        a = a[:, perm].contiguous()
+        op = cls(ctx)
+        op.tensors = {"dense": a}
+        op.n_rows, op.n_global, op.row0, op.row_offsets = n_rows, n_global, row0, list(row_offsets)
+        op.nnz = a.numel()
+        op.kind = "dense"
+        op.n_halo = n_global - n_rows
+        op.h2d_bytes = h2d
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_mat_dense(ctx.handle, C.byref(op.handle), n_rows, n_global, _ptr(a), int(a.stride(0))),
+                  "pk_mat_dense")
+            if world > 1:
+                # peer p sends its whole block; we send ours to everyone
+                send_off, recv_off = [0], [0]
+                for p in range(world):
+                    cnt = row_offsets[p + 1] - row_offsets[p]
+                    send_off.append(send_off[-1] + (n_rows if p != rank else 0))
+                    recv_off.append(recv_off[-1] + (cnt if p != rank else 0))
+                idx = torch.arange(n_rows, dtype=torch.int32).repeat(world - 1)
+                idx_d = idx.to(dev)
+                op.tensors["send_idx"] = idx_d
+                so = np.asarray(send_off, dtype=np.int64)
+                ro = np.asarray(recv_off, dtype=np.int64)
+                check(ctx.lib.pk_mat_set_halo(op.handle, world, so.ctypes.data_as(C.c_void_p),
+                                              ro.ctypes.data_as(C.c_void_p), _ptr(idx_d),
+                                              C.c_void_p(idx.data_ptr()), 0, 0), "pk_mat_set_halo")
+        return op
+
+    @classmethod
+    def from_any_local(cls, local_A, group=None, ctx: Optional[Context] = None) -> "DistOperator":
+        if isinstance(local_A, DistOperator):
+            return local_A
+        if isinstance(local_A, np.ndarray):
+            return cls.from_local_dense(torch.from_numpy(np.ascontiguousarray(local_A, dtype=np.float64)), group, ctx)
+        if isinstance(local_A, torch.Tensor) and local_A.layout == torch.strided:
+            return cls.from_local_dense(local_A, group, ctx)
+        if isinstance(local_A, torch.Tensor) and local_A.layout == torch.sparse_csr:
+            return cls.from_local_csr(local_A.crow_indices(), local_A.col_indices(), local_A.values(),
+                                      local_A.shape[1], group, ctx)
+        if isinstance(local_A, (tuple, list)) and len(local_A) == 4:
+            rp, ci, va, n = local_A
+            as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            return cls.from_local_csr(as_t(rp), as_t(ci), as_t(va), int(n), group, ctx)
+        if hasattr(local_A, "tocsr"):
+            m = local_A.tocsr()
+            if not m.has_sorted_indices:
+                m = m.sorted_indices()
+            return cls.from_local_csr(torch.from_numpy(np.ascontiguousarray(m.indptr)),
+                                      torch.from_numpy(np.ascontiguousarray(m.indices)),
+                                      torch.from_numpy(np.ascontiguousarray(m.data, dtype=np.float64)),
+                                      m.shape[1], group, ctx)
+        raise PkError(f"unsupported local_A type {type(local_A)!r}")
+
+
+def solve_dist(method: str, comm, local_A, b, x=None, tol=1e-05, maxiter=None, k=0, *, gather_x: bool = True, **kw):
+    """Shared body of the ``(comm, local_A, b, ...)`` entry points (/root/reference/v3/gpu/mpi/cg.py:10).
+
+    ``comm``: a torch.distributed process group (None = WORLD) standing in for the mpi4py communicator.
+    ``b`` / ``x``: full length N on every rank (reference convention) or just this rank's rows.
+    Returns on EVERY rank (the reference returns on rank 0 and calls ``exit(0)`` elsewhere, cg.py:59-68): x is the
+    full-length solution (``gather_x=True``) or this rank's slice."""
+    from .._core import solve
+    if not dist.is_initialized():
+        raise PkError("torch.distributed is not initialised (launch with torchrun, backend nccl)")
+    op = DistOperator.from_any_local(local_A, comm)
+    ctx = op.ctx
+    n, N = op.n_rows, op.n_global
+    lo = op.row0
+
+    def local_part(v):
+        if v is None:
+            return None
+        size = v.size if isinstance(v, np.ndarray) else v.numel()
+        if size == N and N != n:
+            return v[lo:lo + n]
+        if size == n:
+            return v
+        raise PkError(f"vector has {size} entries; expected N={N} or the local {n}")
+
+    b_loc = local_part(b)
+    x_loc = local_part(x) if isinstance(x, (np.ndarray, torch.Tensor)) else None
+    if maxiter is None:
+        maxiter = N
+    x_out, info = solve(method, op, b_loc, x=x_loc, tol=tol, maxiter=maxiter, k=k, ctx=ctx, **kw)
+    if gather_x and ctx.n_ranks > 1:
+        sizes = [op.row_offsets[p + 1] - op.row_offsets[p] for p in range(ctx.n_ranks)]
+        if len(set(sizes)) == 1:
+            full = torch.empty(N, dtype=torch.float64, device=ctx.torch_device)
+            xs = x_out.contiguous()
+            torch.cuda.current_stream(ctx.device).synchronize()
+            check(ctx.lib.pk_allgather(ctx.handle, _ptr(xs), _ptr(full), n), "pk_allgather")
+            ctx.sync()
+        else:
+            mx = max(sizes)                      # uneven blocks: pad to the largest, gather, trim
+            pad = torch.zeros(mx, dtype=torch.float64, device=ctx.torch_device)
+            pad[:n] = x_out
+            parts = [torch.empty(mx, dtype=torch.float64, device=ctx.torch_device) for _ in sizes]
+            dist.all_gather(parts, pad, group=comm)
+            full = torch.cat([p[:s] for p, s in zip(parts, sizes)])
+        x_out = full
+    return x_out, info

@@ -38,11 +38,17 @@ def inputs(case):
 
 
 def history_tolerance(case):
-    """Relative tolerance on the residual history over the first 50 solver iterations
-    (BASELINE.json north_star: 1e-10; k-skip with k>=4 is summation-order sensitive — BASELINE.md §2)."""
+    """(rtol, atol) on the residual history over the first 50 solver iterations, or None.
+
+    BASELINE.json north_star: 1e-10 relative.  That holds for cg / mrr / k <= 2 (measured on B200: <= 1e-11).  The
+    k-skip recurrences rebuild every step's scalars from Gram sums of an unscaled monomial basis, so a different
+    (equally valid) summation order moves the history by ~1e-9 relative at k = 4 and by O(1) at k = 8 — the
+    reference disagrees with ITSELF by that much when only its mat-vec summation order changes.
+    k = 3..4: 1e-8 relative plus 1e-11 absolute (residuals are relative to ||b||, i.e. start at 1);
+    k >= 5: judged on iteration count (+-1 trip / 5 %) and the final true residual only."""
     k = case["k"] or 0
     if case["solver"] in ("cg", "mrr") or k <= 2:
-        return 1e-10
+        return (1e-10, 0.0)
     if k <= 4:
-        return 1e-6
-    return None  # k >= 8: monomial basis amplifies rounding to O(1); judged on count and true residual
+        return (1e-8, 1e-11)
+    return None

@@ -21,7 +21,7 @@ def test_oracle_matches_reference_golden(case):
     tol = history_tolerance(case)
     if tol is not None:
         assert np.array_equal(info["nosl"], gold["nosl"])
-        np.testing.assert_allclose(info["residual"], gold["residual"], rtol=1e-11, atol=0)
+        np.testing.assert_allclose(info["residual"], gold["residual"], rtol=max(1e-11, tol[0] * 0.1), atol=tol[1])
         if "x" in gold:
             np.testing.assert_allclose(x, gold["x"], rtol=1e-9, atol=1e-12 * np.abs(gold["x"]).max())
         else:
@@ -49,3 +49,17 @@ def test_oracle_is_bitwise_on_generating_machine():
             same += 1
     # OpenBLAS threading differs between hosts; require the overwhelming majority, not all.
     assert same >= 30, same
+
+
+def test_c_restatement_of_csr_matvec_matches_scipy_bitwise():
+    """oracle/oracle_kernels.c (plain-C csr_matvec, stencil generator) against scipy / problems.py."""
+    import host_kernels as hk
+    from parallel_krylov_b200 import problems
+    for gen, args in ((problems.poisson3d, (9, 7, 5)), (problems.poisson2d, (31,)), (problems.banded_spd, (999, 13, 0))):
+        rowptr, col, val, n = gen(*args)
+        x = np.random.default_rng(0).standard_normal(n)
+        assert np.array_equal(hk.csr_matvec(rowptr, col, val, x), problems.to_scipy(rowptr, col, val, n).dot(x))
+    for dims in ((9, 7, 5), (31, 31, 1), (4, 1, 1)):
+        r, c, v, n = hk.stencil_csr(*dims)
+        hr, hc, hv, hn = problems.poisson3d(*dims) if dims[2] > 1 else problems._stencil_csr(dims[:2], 4.0)
+        assert n == hn and np.array_equal(r, hr) and np.array_equal(c, hc) and np.array_equal(v, hv)
