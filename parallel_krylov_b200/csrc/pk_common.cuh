@@ -129,7 +129,9 @@ struct pk_mat {
     // csr-stream tiling
     int tile_rows = 256;     // rows per tile == threads per block
     int tile_cap = 2048;     // nnz capacity of the shared-memory product buffer (per right-hand side)
-    bool vec_ok = true;      // col/val 16-byte aligned: 128-bit loads
+    bool vec_ok = true;      // rowptr/col/val 16-byte aligned: 128-bit loads / bulk copies
+    bool use_tma = true;     // TMA-pipelined kernel (needs vec_ok)
+    int stages = 3;          // ring depth of the TMA pipeline
     // halo plan
     bool distributed = false;
     long long n_halo = 0;

@@ -4,6 +4,10 @@
 #include "pk_device.cuh"
 #include "pk_launch.h"
 
+#include <stdlib.h>
+
+#include <map>
+
 namespace {
 
 constexpr int EW_BLOCK = 256;
@@ -186,9 +190,11 @@ __global__ void k_set_k(PkState* st, int k) {
     if (st->khist && st->idx < st->hist_len) st->khist[st->idx] = k;   // adaptivekskipmrr.py:66
 }
 
-inline int ew_grid(pk_ctx* ctx, long long n) {
-    long long want = (n + EW_BLOCK * 4 - 1) / (EW_BLOCK * 4);
-    long long cap = (long long)ctx->sm_count * 8;
+// persistent grid: one full wave of resident blocks (or fewer when the vector is short)
+template <class K>
+inline int ew_grid(pk_ctx* ctx, K kernel, long long n, int per_thread = 2) {
+    long long want = (n + EW_BLOCK * per_thread - 1) / (EW_BLOCK * per_thread);
+    long long cap = (long long)ctx->sm_count * pk_blocks_per_sm((const void*)kernel, EW_BLOCK, 0);
     if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
@@ -222,6 +228,21 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
+int pk_blocks_per_sm(const void* kernel, int block, size_t smem) {
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    auto key = std::make_pair(kernel, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    cache[key] = per_sm;
+    return per_sm;
+}
+
 int pk_launch_scalar(pk_ctx* ctx, int epi, int ignore_done) {
     k_scalar<<<1, 1, 0, ctx->stream>>>(ctx->d_state, epi, ignore_done);
     PK_LAUNCH_CHECK();
@@ -245,52 +266,52 @@ int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done
 }
 
 int pk_launch_dot(pk_ctx* ctx, long long n, const double* u, const double* v, int epi, int ignore_done) {
-    k_dot<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, u, v, red_args(ctx, epi), ignore_done);
+    k_dot<<<ew_grid(ctx, k_dot, n), EW_BLOCK, 0, ctx->stream>>>(n, u, v, red_args(ctx, epi), ignore_done);
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, ignore_done);
 }
 
 int pk_launch_resid_init(pk_ctx* ctx, long long n, const double* b, const double* v, double* r, double* p, int epi) {
-    k_resid_init<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, b, v, r, p, red_args(ctx, epi));
+    k_resid_init<<<ew_grid(ctx, k_resid_init, n), EW_BLOCK, 0, ctx->stream>>>(n, b, v, r, p, red_args(ctx, epi));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v) {
-    k_cg_xr<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args(ctx, EPI_CG_BETA));
+    k_cg_xr<<<ew_grid(ctx, k_cg_xr, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args(ctx, EPI_CG_BETA));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, EPI_CG_BETA, -1, 0);
 }
 
 int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r) {
-    k_cg_p<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, p, r, ctx->d_state);
+    k_cg_p<<<ew_grid(ctx, k_cg_p, n), EW_BLOCK, 0, ctx->stream>>>(n, p, r, ctx->d_state);
     PK_LAUNCH_CHECK();
     return PK_OK;
 }
 
 int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
                         int epi) {
-    k_mrr_first<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, r, x, y, z, red_args(ctx, epi));
+    k_mrr_first<<<ew_grid(ctx, k_mrr_first, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, r, x, y, z, red_args(ctx, epi));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r) {
-    k_mrr_s<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args(ctx, EPI_MRR_ZETA));
+    k_mrr_s<<<ew_grid(ctx, k_mrr_s, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args(ctx, EPI_MRR_ZETA));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
 }
 
 int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
                          int cj, int epi) {
-    k_mrr_update<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args(ctx, epi));
+    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args(ctx, epi));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
                           int epi) {
-    k_kscg_update<<<ew_grid(ctx, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args(ctx, epi));
+    k_kscg_update<<<ew_grid(ctx, k_kscg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args(ctx, epi));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
@@ -299,11 +320,7 @@ namespace {
 template <int W, int MODE>
 int gram_window(pk_ctx* ctx, long long n, long long ld, const double* U, int nu, const double* V, int nv, int j0,
                 int epi) {
-    // register-heavy kernel (6W accumulators): fewer, fatter blocks
-    long long cap = (long long)ctx->sm_count * (W <= 4 ? 4 : 2);
-    long long want = (n + EW_BLOCK - 1) / EW_BLOCK;
-    if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
-    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    int grid = ew_grid(ctx, k_gram<W, MODE>, n, 1);   // register-heavy (6W accumulators): occupancy decides the grid
     k_gram<W, MODE><<<grid, EW_BLOCK, 0, ctx->stream>>>(n, ld, U, nu, V, nv, j0, red_args(ctx, epi, 6 * j0));
     PK_LAUNCH_CHECK();
     return PK_OK;
@@ -332,7 +349,12 @@ int gram_dispatch(pk_ctx* ctx, int w, long long n, long long ld, const double* U
 // final_epi runs once everything is reduced (EPI_GRAM_CG / EPI_GRAM_MRR / EPI_NONE).
 int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const double* U, int nu, const double* V, int nv,
                    int njj, int final_epi) {
-    constexpr int WMAX = 10;
+    static int WMAX = 0;
+    if (WMAX == 0) {
+        const char* e = getenv("PK_GRAM_W");
+        WMAX = e ? atoi(e) : 10;
+        if (WMAX < 1 || WMAX > 10) WMAX = 10;
+    }
     int j0 = 0;
     while (j0 < njj) {
         int w = njj - j0 < WMAX ? njj - j0 : WMAX;

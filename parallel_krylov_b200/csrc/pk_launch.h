@@ -2,6 +2,10 @@
 #pragma once
 #include "pk_common.cuh"
 
+// Resident blocks per SM of a kernel (occupancy API, cached): persistent grids are sized sm_count x this, so that a
+// grid-stride kernel runs as exactly one full wave (a partial second wave costs up to 2x on these streaming kernels).
+int pk_blocks_per_sm(const void* kernel, int block, size_t smem);
+
 // pk_kernels.cu — fused vector kernels; every reducing launch is followed (multi-GPU) by all-reduce + scalar engine
 int pk_launch_scalar(pk_ctx* ctx, int epi, int ignore_done);
 int pk_launch_set_k(pk_ctx* ctx, int k);
@@ -26,6 +30,7 @@ struct PkDots {
     int epi = EPI_NONE;
 };
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
+int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result);
 
 // pk_comm.cu — NCCL over NVLink
 int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s);

@@ -4,6 +4,7 @@
 // `if residual[i] < tol` on a cupy scalar, /root/reference/v3/gpu/cg.py:26).  Kernels enqueued after the stopping
 // rule fired are no-ops, so x, the history and the iteration count are exactly those of the reference loop.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -143,22 +144,29 @@ extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_c
     m->rowptr = d_rowptr;
     m->col = d_col;
     m->val = d_val;
-    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0);
+    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0) && (((uintptr_t)d_rowptr & 15) == 0);
     // Kernel choice from the nnz distribution (mean row length): tiles of 256 rows (128 for mid-length rows) staged in
     // shared memory when a tile's nonzeros fit; otherwise the warp-per-row path handles the tile.
     const double mean = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
-    if (mean <= 12.0) {
-        m->tile_rows = 256;
-        m->tile_cap = (int)round_up((long long)std::max(512.0, 256 * mean * 1.15 + 64), 256);
-        m->kind = MAT_CSR_STREAM;
-    } else if (mean <= 40.0) {
-        m->tile_rows = 128;
-        m->tile_cap = (int)round_up((long long)(128 * mean * 1.15 + 64), 256);
+    m->tile_rows = mean <= 12.0 ? 256 : 128;
+    long long heur = (long long)(m->tile_rows * mean * 1.25) + 64;      // room for moderately irregular rows
+    int tile_max = 0;
+    if (n_rows > 0) PK_CHECK(pk_tile_max_nnz(ctx, d_rowptr, n_rows, m->tile_rows, &tile_max));
+    long long cap = std::min<long long>(heur, (long long)tile_max + 3);  // +3: the staged window starts 16-byte aligned
+    cap = std::max<long long>(round_up(cap, 64), 256);
+    if (mean <= 40.0 && cap * 12 <= 96 * 1024) {
+        m->tile_cap = (int)cap;
         m->kind = MAT_CSR_STREAM;
     } else {
-        m->tile_rows = 128;
-        m->tile_cap = 256;        // rows longer than this are reduced warp-per-row
+        m->tile_cap = 256;        // practically every tile exceeds this: rows are reduced warp-per-row
         m->kind = MAT_CSR_VECTOR;
+    }
+    {
+        const char* e = getenv("PK_SPMV");            // "stream": plain-load kernel; default: TMA-pipelined kernel
+        m->use_tma = m->vec_ok && !(e && strcmp(e, "stream") == 0);
+        const char* st = getenv("PK_SPMV_STAGES");
+        m->stages = st ? atoi(st) : 2;
+        if (m->stages < 2 || m->stages > 4) m->stages = 2;
     }
     m->ld = round_up(std::max<long long>(n_rows, n_cols_local), 32);
     *out = m;

@@ -4,10 +4,12 @@
 // cupy.dot launches that follow it (/root/reference/v3/gpu/cg.py:31-32).
 //
 // CSR-stream kernel (short rows: stencils, bands): a block owns a tile of BLOCK consecutive rows.  Phase 1 streams the
-// tile's nonzeros with 128-bit coalesced loads (int4 of column indices, 2 x double2 of values), gathers x through the
-// read-only path and parks val*x in shared memory.  Phase 2: thread t adds up row t's products left to right — the
-// accumulation order of scipy's csr_matvec, which makes y bit-identical to the oracle's A.dot(x) (products and sums
-// are separately rounded: the library is built with -fmad=false).  Tiles whose nonzeros exceed the staging buffer
+// tile's nonzeros with 128-bit coalesced loads (int4 of column indices, 2 x double2 of values) into shared memory.
+// Phase 2: thread t walks row t left to right, gathering x through the read-only path — neighbouring lanes are
+// neighbouring rows, so on banded/stencil structure a warp's gather touches 2-3 cache lines instead of ~14 when the
+// gather is done in nonzero order (ncu r01: that version was L1-wavefront bound at 64 % of HBM peak).  The
+// accumulation order is that of scipy's csr_matvec, which makes y bit-identical to the oracle's A.dot(x) (products
+// and sums are separately rounded: the library is built with -fmad=false).  Tiles whose nonzeros exceed the staging buffer
 // (long rows) are processed warp-per-row with a shuffle reduction instead.
 // Dense kernel: warp per row, 128-bit loads, no tensor cores (GEMV is HBM-bound).
 #include "pk_device.cuh"
@@ -26,8 +28,10 @@ struct SpmvArgs {
     double* y0;
     double* y1;
     const double* w;        // fused dots against this vector (nullable)
+    int w_is_x;             // w == x0 (CG's p.Ap): take w[row] from the diagonal gather instead of loading it again
     long long row_lo, row_hi;
     long long nnz_total;
+    long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
     int reduce;             // 1: run the grid reduction (3 sums)
 };
@@ -35,12 +39,12 @@ struct SpmvArgs {
 template <int NV, int BLOCK, bool VEC>
 __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra) {
     if (pk_done(ra.st)) return;
-    extern __shared__ double prod[];          // [NV][cap]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sval = reinterpret_cast<double*>(smem_raw);              // [cap]
+    int* scol = reinterpret_cast<int*>(sval + a.cap);                // [cap]
     __shared__ int rp[BLOCK + 1];
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* prod0 = prod;
-    double* prod1 = prod + a.cap;
     double acc[3] = {0.0, 0.0, 0.0};
     const long long n_rows = a.row_hi - a.row_lo;
     const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
@@ -51,54 +55,59 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra)
         for (int t = tid; t <= nr; t += BLOCK) rp[t] = a.rowptr[r0 + t];
         __syncthreads();
         const int base = rp[0], end = rp[nr];
-        if (end - base <= a.cap) {
-            // ---- phase 1: stream the tile's nonzeros, stage val * x[col] -------------------------------------
+        const int q0 = VEC ? (base & ~3) : base;                     // 16-byte aligned start of the staged window
+        if (end - q0 <= a.cap) {
+            // ---- phase 1: stream the tile's (col, val) into shared memory, 128-bit coalesced ------------------
             if (VEC) {
-                const int q0 = base & ~3;
                 for (int q = q0 + 4 * tid; q < end; q += 4 * BLOCK) {
-                    int c[4];
-                    double v[4];
+                    const int i = q - q0;
                     if ((long long)q + 4 <= a.nnz_total) {
                         const int4 c4 = __ldg(reinterpret_cast<const int4*>(a.col + q));
                         const double2 v01 = __ldg(reinterpret_cast<const double2*>(a.val + q));
                         const double2 v23 = __ldg(reinterpret_cast<const double2*>(a.val + q + 2));
-                        c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
-                        v[0] = v01.x; v[1] = v01.y; v[2] = v23.x; v[3] = v23.y;
+                        *reinterpret_cast<int4*>(scol + i) = c4;
+                        *reinterpret_cast<double2*>(sval + i) = v01;
+                        *reinterpret_cast<double2*>(sval + i + 2) = v23;
                     } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const bool ok = (long long)q + e < a.nnz_total;
-                            c[e] = ok ? a.col[q + e] : 0;
-                            v[e] = ok ? a.val[q + e] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int idx = q + e;
-                        if (idx >= base && idx < end) {
-                            prod0[idx - base] = v[e] * __ldg(a.x0 + c[e]);
-                            if (NV == 2) prod1[idx - base] = v[e] * __ldg(a.x1 + c[e]);
+                        for (int e = 0; e < 4 && (long long)q + e < a.nnz_total; ++e) {
+                            scol[i + e] = a.col[q + e];
+                            sval[i + e] = a.val[q + e];
                         }
                     }
                 }
             } else {
                 for (int q = base + tid; q < end; q += BLOCK) {
-                    const int c = a.col[q];
-                    const double v = a.val[q];
-                    prod0[q - base] = v * __ldg(a.x0 + c);
-                    if (NV == 2) prod1[q - base] = v * __ldg(a.x1 + c);
+                    scol[q - q0] = a.col[q];
+                    sval[q - q0] = a.val[q];
                 }
             }
             __syncthreads();
-            // ---- phase 2: one thread per row, left-to-right sum (scipy csr_matvec order) -----------------------
+            // ---- phase 2: one thread per row; x gathered here, so that neighbouring lanes (neighbouring rows) read
+            //      neighbouring x entries on banded/stencil structure; left-to-right sum (scipy csr_matvec order) --
             if (tid < nr) {
-                const int s = rp[tid] - base, e = rp[tid + 1] - base;
-                double sum0 = 0.0, sum1 = 0.0;
-                for (int j = s; j < e; ++j) {
-                    sum0 += prod0[j];
-                    if (NV == 2) sum1 += prod1[j];
-                }
+                const int s = rp[tid] - q0, e = rp[tid + 1] - q0;
                 const long long row = r0 + tid;
+                double sum0 = 0.0, sum1 = 0.0;
+                // batches of UNR entries: all gathers of a batch are in flight before the (ordered) accumulation
+                constexpr int UNR = 8;
+                for (int j = s; j < e; j += UNR) {
+                    double vv[UNR], xa[UNR], xb[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const bool ok = j + u < e;
+                        const int c = ok ? scol[j + u] : 0;
+                        vv[u] = ok ? sval[j + u] : 0.0;
+                        xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
+                        if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        if (j + u < e) {
+                            sum0 += vv[u] * xa[u];
+                            if (NV == 2) sum1 += vv[u] * xb[u];
+                        }
+                    }
+                }
                 a.y0[row] = sum0;
                 if (NV == 2) a.y1[row] = sum1;
                 if (a.w) {
@@ -137,7 +146,218 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra)
                 }
             }
         }
-        __syncthreads();   // rp / prod are reused by the next tile
+        __syncthreads();   // rp / staging buffers are reused by the next tile
+    }
+    if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// TMA-pipelined variant (the default on B200).  Same tiling and the same per-row arithmetic as k_spmv_stream, but the
+// tile's rowptr / col / val windows are brought in by 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) into a ring of
+// STAGES shared-memory buffers, completion signalled on an mbarrier per stage.  One thread issues the copies for tile
+// i+STAGES-1 while all threads run the row phase of tile i, so HBM requests stay in flight regardless of how long the
+// row phase takes; the CSR arrays never pass through registers.  A tile that cannot be bulk-copied (window crosses the
+// end of the arrays, or longer than the stage: long rows) is fetched/processed by the plain paths below.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TileMeta {
+    int q0;       // first staged nonzero (16-byte aligned index)
+    int ra0;      // first staged rowptr entry (aligned row index, relative to the range: may be < r0)
+    int bulk;     // 1: the stage holds rowptr/col/val of this tile; 0: plain path
+    int pad;
+};
+
+template <int NV, int BLOCK, int STAGES>
+__global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    __shared__ TileMeta meta[STAGES];
+    constexpr int RP = BLOCK + 8;                                    // staged rowptr entries per tile (aligned window)
+    const size_t stage_bytes = (((size_t)a.cap * 12 + RP * 4) + 127) / 128 * 128;
+    auto st_val = [&](int s) { return reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes); };
+    auto st_col = [&](int s) { return reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes + (size_t)a.cap * 8); };
+    auto st_rp = [&](int s) { return reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes + (size_t)a.cap * 12); };
+    constexpr int NW = BLOCK / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const long long n_rows = a.row_hi - a.row_lo;
+    const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
+    const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // thread 0: issue the bulk copies of my i-th tile into stage i % STAGES (endpoints nb/ne already loaded)
+    auto issue = [&](long long i, int nb, int ne) {
+        const int s = (int)(i % STAGES);
+        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long r0 = a.row_lo + tile * BLOCK;
+        const int nr = (int)((a.row_hi - r0) < BLOCK ? (a.row_hi - r0) : BLOCK);
+        const int q0 = nb & ~3;
+        const int cnt = (ne - q0 + 3) & ~3;
+        const long long ra0 = r0 & ~3LL;
+        const int rcnt = (int)((r0 - ra0) + nr + 1 + 3) & ~3;
+        const bool ok = cnt <= a.cap && (long long)q0 + cnt <= a.nnz_total && ra0 + rcnt <= a.rowptr_len;
+        meta[s].q0 = q0;
+        meta[s].ra0 = (int)(r0 - ra0);
+        meta[s].bulk = ok ? 1 : 0;
+        if (ok) {
+            mbar_expect_tx(&full[s], (unsigned)(cnt * 12 + rcnt * 4));
+            bulk_g2s(st_rp(s), a.rowptr + ra0, (unsigned)(rcnt * 4), &full[s]);
+            if (cnt > 0) {
+                bulk_g2s(st_col(s), a.col + q0, (unsigned)(cnt * 4), &full[s]);
+                bulk_g2s(st_val(s), a.val + q0, (unsigned)(cnt * 8), &full[s]);
+            }
+        } else {
+            mbar_arrive(&full[s]);
+        }
+    };
+    auto endpoints = [&](long long i, int& nb, int& ne) {
+        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long r0 = a.row_lo + tile * BLOCK;
+        const long long r1 = (r0 + BLOCK < a.row_hi) ? r0 + BLOCK : a.row_hi;
+        nb = __ldg(a.rowptr + r0);
+        ne = __ldg(a.rowptr + r1);
+    };
+
+    int nb = 0, ne = 0;          // endpoints of the next tile to issue (thread 0)
+    if (tid == 0) {
+        for (long long i = 0; i < STAGES - 1 && i < my_tiles; ++i) {
+            endpoints(i, nb, ne);
+            issue(i, nb, ne);
+        }
+        if (STAGES - 1 < my_tiles) endpoints(STAGES - 1, nb, ne);
+    }
+
+    for (long long i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i % STAGES);
+        if (tid == 0) {
+            const long long nxt = i + STAGES - 1;
+            if (nxt < my_tiles) {
+                issue(nxt, nb, ne);
+                if (nxt + 1 < my_tiles) endpoints(nxt + 1, nb, ne);   // consumed next iteration: latency hidden
+            }
+        }
+        mbar_wait(&full[s], (unsigned)((i / STAGES) & 1));
+        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long r0 = a.row_lo + tile * BLOCK;
+        const int nr = (int)((a.row_hi - r0) < BLOCK ? (a.row_hi - r0) : BLOCK);
+        double* sval = st_val(s);
+        int* scol = st_col(s);
+        int* rp = st_rp(s);
+        int q0 = meta[s].q0;
+        int rofs = meta[s].ra0;
+        bool staged = meta[s].bulk != 0;
+        if (!staged) {
+            // plain fetch of this tile (array tail or long rows)
+            rofs = 0;
+            for (int t = tid; t <= nr; t += BLOCK) rp[t] = a.rowptr[r0 + t];
+            __syncthreads();
+            const int base = rp[0], end = rp[nr];
+            q0 = base;
+            if (end - base <= a.cap) {
+                for (int q = base + tid; q < end; q += BLOCK) {
+                    scol[q - base] = a.col[q];
+                    sval[q - base] = a.val[q];
+                }
+                staged = true;
+            }
+            __syncthreads();
+        }
+        if (staged) {
+            if (tid < nr) {
+                const int sb = rp[rofs + tid] - q0, se = rp[rofs + tid + 1] - q0;
+                const long long row = r0 + tid;
+                const double wi = a.w ? __ldg(a.w + row) : 0.0;      // issued before the row loop: latency hidden
+                double sum0 = 0.0, sum1 = 0.0;
+                constexpr int UNR = 8;
+                for (int j = sb; j < se; j += UNR) {
+                    double vv[UNR], xa[UNR], xb[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const bool ok = j + u < se;
+                        const int c = ok ? scol[j + u] : 0;
+                        vv[u] = ok ? sval[j + u] : 0.0;
+                        xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
+                        if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        if (j + u < se) {
+                            sum0 += vv[u] * xa[u];
+                            if (NV == 2) sum1 += vv[u] * xb[u];
+                        }
+                    }
+                }
+                a.y0[row] = sum0;
+                if (NV == 2) a.y1[row] = sum1;
+                if (a.w) {
+                    acc[0] += wi * sum0;
+                    acc[1] += sum0 * sum0;
+                    acc[2] += wi * wi;
+                }
+            }
+        } else {
+            for (int r = warp; r < nr; r += NW) {
+                const int sb = rp[r], se = rp[r + 1];
+                double sum0 = 0.0, sum1 = 0.0;
+                for (int q = sb + lane; q < se; q += 32) {
+                    const int c = a.col[q];
+                    const double v = a.val[q];
+                    sum0 += v * __ldg(a.x0 + c);
+                    if (NV == 2) sum1 += v * __ldg(a.x1 + c);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    sum0 += __shfl_down_sync(0xffffffffu, sum0, off);
+                    if (NV == 2) sum1 += __shfl_down_sync(0xffffffffu, sum1, off);
+                }
+                if (lane == 0) {
+                    const long long row = r0 + r;
+                    a.y0[row] = sum0;
+                    if (NV == 2) a.y1[row] = sum1;
+                    if (a.w) {
+                        const double wi = a.w[row];
+                        acc[0] += wi * sum0;
+                        acc[1] += sum0 * sum0;
+                        acc[2] += wi * wi;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with stage s: thread 0 may refill it next iteration
     }
     if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
 }
@@ -215,13 +435,7 @@ __global__ void __launch_bounds__(BLOCK) k_gemv(GemvArgs a, PkRedArgs ra) {
 
 template <int NV, int BLOCK, bool VEC>
 int stream_grid(pk_ctx* ctx, size_t smem, long long n_tiles) {
-    static int per_sm_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int per_sm = 0;
-    auto kern = k_spmv_stream<NV, BLOCK, VEC>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    (void)per_sm_cache;
+    const int per_sm = pk_blocks_per_sm((const void*)k_spmv_stream<NV, BLOCK, VEC>, BLOCK, smem);
     long long g = (long long)ctx->sm_count * per_sm;
     if (g > n_tiles) g = n_tiles;
     if (g < 1) g = 1;
@@ -231,7 +445,7 @@ int stream_grid(pk_ctx* ctx, size_t smem, long long n_tiles) {
 // mode 0: choose the grid and launch; 1: dry run (only report the grid); 2: launch with the grid in *grid_io
 template <int NV, int BLOCK, bool VEC>
 int launch_stream(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int grid_cap, int mode) {
-    const size_t smem = (size_t)NV * a.cap * sizeof(double);
+    const size_t smem = (size_t)a.cap * (sizeof(double) + sizeof(int));
     const long long n_rows = a.row_hi - a.row_lo;
     if (n_rows <= 0) { *grid_io = 0; return PK_OK; }
     const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
@@ -252,8 +466,8 @@ int launch_stream(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, in
     return PK_OK;
 }
 
-int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap,
-                      int mode) {
+int launch_plain_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap,
+                     int mode) {
     const bool vec = m->vec_ok;
     if (m->tile_rows == 128) {
         if (two) return vec ? launch_stream<2, 128, true>(ctx, a, ra, grid_io, cap, mode)
@@ -267,10 +481,65 @@ int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRed
                : launch_stream<1, 256, false>(ctx, a, ra, grid_io, cap, mode);
 }
 
+// ---- TMA variant launcher ------------------------------------------------------------------------------------------
+template <int NV, int BLOCK, int STAGES>
+int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int grid_cap, int mode) {
+    const size_t stage_bytes = (((size_t)a.cap * 12 + (BLOCK + 8) * 4) + 127) / 128 * 128;
+    const size_t smem = stage_bytes * STAGES;
+    const long long n_rows = a.row_hi - a.row_lo;
+    if (n_rows <= 0) { *grid_io = 0; return PK_OK; }
+    const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
+    int grid = *grid_io;
+    if (mode != 2) {
+        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES>, BLOCK, smem);
+        long long g = (long long)ctx->sm_count * per_sm;
+        if (g > n_tiles) g = n_tiles;
+        if (g > grid_cap) g = grid_cap;
+        grid = (int)(g < 1 ? 1 : g);
+        *grid_io = grid;
+        if (mode == 1) return PK_OK;
+    } else {
+        pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES>, BLOCK, smem);   // sets the smem attribute
+    }
+    k_spmv_tma<NV, BLOCK, STAGES><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pk_set_error("spmv(tma) launch (grid %d, smem %zu): %s", grid, smem, cudaGetErrorString(e));
+        return PK_ERR_CUDA;
+    }
+    ctx->launches++;
+    return PK_OK;
+}
+
+template <int NV, int BLOCK>
+int launch_tma_stages(pk_ctx* ctx, int stages, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
+    switch (stages) {
+        case 2: return launch_tma<NV, BLOCK, 2>(ctx, a, ra, grid_io, cap, mode);
+        case 4: return launch_tma<NV, BLOCK, 4>(ctx, a, ra, grid_io, cap, mode);
+        default: return launch_tma<NV, BLOCK, 3>(ctx, a, ra, grid_io, cap, mode);
+    }
+}
+
+int launch_tma_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
+    if (m->tile_rows == 128) {
+        return two ? launch_tma_stages<2, 128>(ctx, m->stages, a, ra, grid_io, cap, mode)
+                   : launch_tma_stages<1, 128>(ctx, m->stages, a, ra, grid_io, cap, mode);
+    }
+    return two ? launch_tma_stages<2, 256>(ctx, m->stages, a, ra, grid_io, cap, mode)
+               : launch_tma_stages<1, 256>(ctx, m->stages, a, ra, grid_io, cap, mode);
+}
+
+int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap,
+                      int mode) {
+    if (m->use_tma) return launch_tma_any(ctx, m, two, a, ra, grid_io, cap, mode);
+    return launch_plain_any(ctx, m, two, a, ra, grid_io, cap, mode);
+}
+
 int launch_gemv(pk_ctx* ctx, pk_mat* m, bool two, const GemvArgs& a, PkRedArgs ra) {
     constexpr int BLOCK = 256;
     long long want = (a.n_rows + (BLOCK / 32) - 1) / (BLOCK / 32);
-    long long cap = (long long)ctx->sm_count * 8;
+    long long cap = (long long)ctx->sm_count *
+                    pk_blocks_per_sm(two ? (const void*)k_gemv<2, BLOCK> : (const void*)k_gemv<1, BLOCK>, BLOCK, 0);
     if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     if (two) k_gemv<2, BLOCK><<<grid, BLOCK, 0, ctx->stream>>>(a, ra);
@@ -285,7 +554,39 @@ int launch_gemv(pk_ctx* ctx, pk_mat* m, bool two, const GemvArgs& a, PkRedArgs r
     return PK_OK;
 }
 
+__global__ void k_tile_max(const int32_t* __restrict__ rowptr, long long n_rows, int tile_rows, int* out) {
+    const long long n_tiles = (n_rows + tile_rows - 1) / tile_rows;
+    int m = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
+        const long long r0 = t * tile_rows, r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
+        const int c = rowptr[r1] - rowptr[r0];
+        m = c > m ? c : m;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const int o = __shfl_down_sync(0xffffffffu, m, off);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 }  // namespace
+
+// Largest number of nonzeros in any tile of `tile_rows` consecutive rows (one small pass over rowptr, blocking).
+int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result) {
+    int* d = nullptr;
+    PK_CUDA(cudaMalloc(&d, sizeof(int)));
+    PK_CUDA(cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+    const long long n_tiles = (n_rows + tile_rows - 1) / tile_rows;
+    int grid = (int)((n_tiles + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_tile_max<<<grid, 256, 0, ctx->stream>>>(rowptr, n_rows, tile_rows, d);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(result, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return PK_OK;
+}
 
 static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots);
 
@@ -338,7 +639,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     SpmvArgs a;
     a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
     a.x0 = x; a.x1 = x1; a.y0 = y; a.y1 = y1; a.w = dots.w;
+    a.w_is_x = (dots.w == x) ? 1 : 0;
     a.nnz_total = m->nnz;
+    a.rowptr_len = m->n_rows + 1;
     a.cap = m->tile_cap;
     a.reduce = dots.w ? 1 : 0;
     int grid = 0;
