@@ -230,10 +230,22 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
 // ---------------------------------------------------------------------------------------------------------------
 int pk_blocks_per_sm(const void* kernel, int block, size_t smem) {
     static std::map<std::pair<const void*, size_t>, int> cache;
+    static std::map<const void*, bool> opted_in;
+    if (smem > 40 * 1024 && !opted_in[kernel]) {
+        // opt in ONCE to the device maximum: the attribute is a ceiling for later launches, so it must never be lowered
+        int dev = 0, max_optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        int stat = 1024;
+        if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - stat) != cudaSuccess)
+            cudaGetLastError();   // do not leave a stale error for the next launch check
+        opted_in[kernel] = true;
+    }
     auto key = std::make_pair(kernel, smem);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    if (smem > 40 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();

@@ -1,0 +1,84 @@
+"""Multi-GPU parity worker: launched by tests/test_gpu_dist.py (or by hand) as
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/dist_worker.py
+Every rank solves its row block through parallel_krylov_b200.mpi.* and checks the result against the oracle run on
+the global system (same tolerances as the single-GPU parity tests)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+os.environ.setdefault("PK_QUIET", "1")
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import krylov_oracle as oracle
+from parallel_krylov_b200 import problems
+from parallel_krylov_b200 import mpi as pkm
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    failures = []
+    mats = {
+        "p3d20": problems.to_scipy(*problems.poisson3d(20)),
+        "p3d_9x7x11": problems.to_scipy(*problems.poisson3d(9, 7, 11)),       # rows not divisible by the ranks
+        "band27": problems.to_scipy(*problems.banded_spd(30011, 13, 0)),
+        "dense": problems.dense_spd(384, 0),
+    }
+    cases = [("cg", None), ("mrr", None), ("kskipcg", 2), ("kskipmrr", 2), ("kskipmrr", 4), ("adaptivekskipmrr", 4)]
+    for mname, A in mats.items():
+        n = A.shape[0]
+        base = n // world
+        lo = rank * base
+        hi = n if rank == world - 1 else lo + base
+        local = A[lo:hi]
+        b = problems.rhs(n, "randn", 0)
+        for solver, k in cases:
+            kw = {"k": k} if k is not None else {}
+            xo, io = oracle.SOLVERS[solver](A, b.copy(), tol=1e-8, **kw)
+            x, info = getattr(pkm, solver)(None, local, b, tol=1e-8, **kw)
+            x = x.cpu().numpy()
+            res = info["residual"].cpu().numpy()
+            nosl = info["nosl"].cpu().numpy()
+            tag = f"[{mname} {solver} k={k} rank {rank}]"
+            try:
+                assert x.shape[0] == n, "x must be the full-length solution on every rank"
+                it, it_ref = int(nosl[-1]), int(io["nosl"][-1])
+                slack = 2 if k is None else max(k + 1, int(np.ceil(0.05 * it_ref)))
+                assert abs(it - it_ref) <= slack, (it, it_ref)
+                m = min(len(res), len(io["residual"]), int(np.searchsorted(io["nosl"], 50, side="right")))
+                rtol, atol = (1e-10, 0.0) if (k or 0) <= 2 else (1e-8, 1e-11)
+                np.testing.assert_allclose(res[:m], io["residual"][:m], rtol=rtol, atol=atol)
+                tr = oracle.true_relres(A, b, x)
+                assert tr < 1e-8 * (1 + 1e-6), tr
+                assert info["converged"]
+            except AssertionError as e:
+                failures.append(f"{tag} {e!r}"[:400])
+    # a vector given as this rank's slice only, an initial guess, and gather_x=False
+    A = mats["p3d20"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
+    b = problems.rhs(n, "randn", 0); x0 = np.random.default_rng(3).standard_normal(n)
+    xo, io = oracle.cg(A, b, x0.copy(), tol=1e-8)
+    xs, info = pkm.cg(None, A[lo:hi], b[lo:hi], x=x0[lo:hi], tol=1e-8, gather_x=False)
+    if xs.shape[0] != hi - lo or not np.allclose(xs.cpu().numpy(), xo[lo:hi], rtol=1e-6, atol=1e-9):
+        failures.append(f"[slice inputs rank {rank}] mismatch")
+    if abs(int(info["nosl"][-1]) - int(io["nosl"][-1])) > 2:
+        failures.append(f"[slice inputs rank {rank}] iterations {int(info['nosl'][-1])} vs {int(io['nosl'][-1])}")
+
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    for f in failures:
+        print("FAIL", f, flush=True)
+    if rank == 0:
+        print("DIST_PARITY", "OK" if flag.item() == 0 else f"FAILED ({int(flag.item())})", f"world={world}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
