@@ -47,6 +47,17 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "cg_p3d512"
 
 
+# stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL prints its version there) is sent to
+# stderr instead; the JSON goes to a private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -185,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -392,7 +403,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
