@@ -21,6 +21,7 @@ extern "C" {
 #define PK_VERSION 100
 #define PK_KMAX 32            /* largest k of the k-skip solvers */
 #define PK_NCCL_ID_BYTES 128
+#define PK_IPC_HANDLE_BYTES 64
 
 typedef enum {
     PK_OK = 0,
@@ -80,12 +81,26 @@ int pk_mat_kernel_info(pk_mat* mat, int* kind, int* tile_rows, int* tile_cap);
 int pk_mat_set_halo(pk_mat* mat, int n_peers_total, const int64_t* send_off, const int64_t* recv_off,
                     const int32_t* d_send_idx, const int32_t* h_send_idx, int64_t interior_lo, int64_t interior_hi);
 
+/* Optional NVLink push path for the halo (no NCCL, no side stream): each rank exports its halo receive buffer
+ * (pk_mat_halo_p2p_handle), the handles are all-gathered, and pk_mat_halo_p2p_open maps the peers' buffers;
+ * dst_off[q] = where this rank's entries start inside q's halo (q's recv_off[this rank]), peer_nhalo[q] = q's halo
+ * length.  pk_spmv then pushes boundary entries with plain stores + a sequence flag and the boundary rows wait on the
+ * flags inside the SpMV kernel. */
+int pk_mat_halo_p2p_handle(pk_mat* mat, char handle[PK_IPC_HANDLE_BYTES]);
+int pk_mat_halo_p2p_open(pk_mat* mat, const char* handles, const int64_t* dst_off, const int64_t* peer_nhalo);
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* communicator (NCCL over NVLink).  Replaces MultiGpu.joint_mpi(comm) (v3/gpu/mpi/common.py:168-171).
  * libnccl is dlopen'ed from `nccl_path` (the copy torch already loaded); single-GPU use never touches NCCL. */
 int pk_nccl_unique_id(const char* nccl_path, char id[PK_NCCL_ID_BYTES]);
 int pk_comm_init(pk_ctx* ctx, const char* nccl_path, int n_ranks, int rank, const char id[PK_NCCL_ID_BYTES]);
 int pk_comm_destroy(pk_ctx* ctx);
+/* Optional: all-reduce the dot products INSIDE the reducing kernels over NVLink peer memory (one mailbox per rank,
+ * exported with CUDA IPC) instead of ncclAllReduce + a scalar kernel.  pk_p2p_handle returns this rank's 64-byte IPC
+ * handle; after all-gathering the handles, pk_p2p_open(handles = n_ranks x 64 bytes) maps the peers and switches the
+ * context to the fused path.  Returns PK_ERR_UNSUPPORTED (and stays on the NCCL path) if peer mapping fails. */
+int pk_p2p_handle(pk_ctx* ctx, char handle[PK_IPC_HANDLE_BYTES]);
+int pk_p2p_open(pk_ctx* ctx, int n_ranks, int rank, const char* handles);
 int pk_allreduce_sum(pk_ctx* ctx, double* d_buf, int64_t n);           /* in place, fp64 sum */
 int pk_allgather(pk_ctx* ctx, const double* d_send, double* d_recv, int64_t n_per_rank);
 

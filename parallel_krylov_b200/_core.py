@@ -86,6 +86,29 @@ class Context:
         with torch.cuda.device(self.device):
             check(self.lib.pk_comm_init(self.handle, path, world, rank, raw), "pk_comm_init")
         self.n_ranks, self.rank, self.group = world, rank, group
+        self.fused_allreduce = False
+        if os.environ.get("PK_ALLREDUCE", "p2p") != "nccl":
+            self._open_mailboxes(group, world, rank, dev)
+
+    def _open_mailboxes(self, group, world, rank, dev):
+        """Exchange CUDA-IPC handles of the per-rank mailboxes so that the reducing kernels can all-reduce their dot
+        products themselves over NVLink (csrc/pk_device.cuh).  Falls back to ncclAllReduce if mapping fails."""
+        import torch.distributed as dist
+        hb = C.create_string_buffer(_lib.PK_IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            check(self.lib.pk_p2p_handle(self.handle, hb), "pk_p2p_handle")
+        mine = torch.tensor(list(hb.raw), dtype=torch.uint8, device=dev)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        with torch.cuda.device(self.device):
+            rc = self.lib.pk_p2p_open(self.handle, world, rank, raw)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            self.fused_allreduce = True
+        else:   # all ranks must agree on the path
+            raise PkError("peer mapping of the all-reduce mailboxes failed on some rank; set PK_ALLREDUCE=nccl")
 
 
 def _find_nccl() -> str:

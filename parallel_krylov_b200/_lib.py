@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpkrylov.so")
 
 PK_KMAX = 32
 PK_NCCL_ID_BYTES = 128
+PK_IPC_HANDLE_BYTES = 64
 PK_CG, PK_MRR, PK_KSKIPCG, PK_KSKIPMRR, PK_ADAPTIVEKSKIPMRR = range(5)
 METHOD_IDS = {"cg": PK_CG, "mrr": PK_MRR, "kskipcg": PK_KSKIPCG, "kskipmrr": PK_KSKIPMRR,
               "adaptivekskipmrr": PK_ADAPTIVEKSKIPMRR}
@@ -46,9 +47,13 @@ _SIGS = {
     "pk_mat_kernel_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pk_mat_ld": (_I64, [_P]),
     "pk_mat_set_halo": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _I64, _I64]),
+    "pk_mat_halo_p2p_handle": (C.c_int, [_P, C.c_char_p]),
+    "pk_mat_halo_p2p_open": (C.c_int, [_P, C.c_char_p, _P, _P]),
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "pk_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "pk_comm_destroy": (C.c_int, [_P]),
+    "pk_p2p_handle": (C.c_int, [_P, C.c_char_p]),
+    "pk_p2p_open": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
     "pk_allreduce_sum": (C.c_int, [_P, _P, _I64]),
     "pk_allgather": (C.c_int, [_P, _P, _P, _I64]),
     "pk_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),

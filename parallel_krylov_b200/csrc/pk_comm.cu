@@ -10,6 +10,8 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "pk_common.cuh"
 #include "pk_launch.h"
 
@@ -99,7 +101,149 @@ extern "C" int pk_comm_init(pk_ctx* ctx, const char* nccl_path, int n_ranks, int
     return PK_OK;
 }
 
+// ---- NVLink mailboxes for the in-kernel all-reduce ------------------------------------------------------------------
+// Each rank allocates its mailbox with cudaMalloc, exports it with CUDA IPC; after the handles have been all-gathered
+// (torch.distributed, host side) every rank maps its peers' mailboxes.  From then on the reducing kernels all-reduce
+// their sums themselves (pk_device.cuh) and neither ncclAllReduce nor the 1-thread scalar kernel is launched.
+extern "C" int pk_p2p_handle(pk_ctx* ctx, char handle[PK_IPC_HANDLE_BYTES]) {
+    PK_REQUIRE(ctx != nullptr && handle != nullptr, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PK_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->my_mbox) {
+        PK_CUDA(cudaMalloc(&ctx->my_mbox, PK_MBOX_DOUBLES * sizeof(double)));
+        PK_CUDA(cudaMemset(ctx->my_mbox, 0, PK_MBOX_DOUBLES * sizeof(double)));
+    }
+    cudaIpcMemHandle_t h;
+    PK_CUDA(cudaIpcGetMemHandle(&h, ctx->my_mbox));
+    memcpy(handle, &h, PK_IPC_HANDLE_BYTES);
+    return PK_OK;
+}
+
+extern "C" int pk_p2p_open(pk_ctx* ctx, int n_ranks, int rank, const char* handles) {
+    PK_REQUIRE(ctx != nullptr && handles != nullptr, "null argument");
+    PK_REQUIRE(n_ranks >= 2 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
+    PK_REQUIRE(ctx->my_mbox != nullptr, "call pk_p2p_handle first");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PkP2P h;
+    memset(&h, 0, sizeof(h));
+    h.n_ranks = n_ranks;
+    h.rank = rank;
+    for (int p = 0; p < n_ranks; ++p) {
+        if (p == rank) {
+            h.mbox[p] = ctx->my_mbox;
+            continue;
+        }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles + (size_t)p * PK_IPC_HANDLE_BYTES, PK_IPC_HANDLE_BYTES);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pk_set_error("cudaIpcOpenMemHandle(rank %d -> %d): %s", rank, p, cudaGetErrorString(e));
+            for (void* q : ctx->peer_mbox) cudaIpcCloseMemHandle(q);
+            ctx->peer_mbox.clear();
+            return PK_ERR_UNSUPPORTED;
+        }
+        ctx->peer_mbox.push_back(ptr);
+        h.mbox[p] = (double*)ptr;
+    }
+    PK_CUDA(cudaMalloc(&h.seq, sizeof(unsigned long long)));
+    PK_CUDA(cudaMemset(h.seq, 0, sizeof(unsigned long long)));
+    PkP2P* d = nullptr;
+    PK_CUDA(cudaMalloc(&d, sizeof(PkP2P)));
+    PK_CUDA(cudaMemcpy(d, &h, sizeof(PkP2P), cudaMemcpyHostToDevice));
+    ctx->d_p2p = d;
+    return PK_OK;
+}
+
+// ---- NVLink halo push: receive buffers ------------------------------------------------------------------------------
+extern "C" int pk_mat_halo_p2p_handle(pk_mat* m, char handle[PK_IPC_HANDLE_BYTES]) {
+    PK_REQUIRE(m != nullptr && handle != nullptr, "null argument");
+    PK_REQUIRE(m->distributed, "pk_mat_set_halo first");
+    PK_CUDA(cudaSetDevice(m->ctx->device));
+    if (!m->d_recvbuf) {
+        const size_t n = PK_HALO_HDR + 4 * (size_t)std::max<long long>(m->n_halo, 1);
+        PK_CUDA(cudaMalloc(&m->d_recvbuf, n * sizeof(double)));
+        PK_CUDA(cudaMemset(m->d_recvbuf, 0, n * sizeof(double)));
+    }
+    cudaIpcMemHandle_t h;
+    PK_CUDA(cudaIpcGetMemHandle(&h, m->d_recvbuf));
+    memcpy(handle, &h, PK_IPC_HANDLE_BYTES);
+    return PK_OK;
+}
+
+// handles: n_ranks x 64 bytes; dst_off[q] = offset of my entries inside q's halo (q's recv_off[me]);
+// peer_nhalo[q] = q's halo length.
+extern "C" int pk_mat_halo_p2p_open(pk_mat* m, const char* handles, const int64_t* dst_off, const int64_t* peer_nhalo) {
+    PK_REQUIRE(m && handles && dst_off && peer_nhalo, "null argument");
+    PK_REQUIRE(m->d_recvbuf != nullptr, "call pk_mat_halo_p2p_handle first");
+    pk_ctx* ctx = m->ctx;
+    const int P = ctx->n_ranks, me = ctx->rank;
+    PK_REQUIRE(P <= PK_MAX_RANKS, "too many ranks for the push path");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PkHaloPush& hp = m->push;
+    memset(&hp, 0, sizeof(hp));
+    hp.n_ranks = P;
+    hp.me = me;
+    hp.send_idx = m->d_send_idx;
+    for (int q = 0; q <= P; ++q) hp.send_off[q] = m->send_off[q];
+    for (int q = 0; q < P; ++q) {
+        hp.dst_off[q] = dst_off[q];
+        hp.peer_nhalo[q] = peer_nhalo[q];
+        hp.send_first[q] = m->send_first[q];
+        hp.send_contig[q] = m->send_contig[q];
+        if (m->recv_off[q + 1] > m->recv_off[q]) hp.recv_mask |= (1u << q);
+        if (q == me) { hp.peer_recv[q] = m->d_recvbuf; continue; }
+        const bool needed = m->send_off[q + 1] > m->send_off[q];
+        if (!needed) continue;                      // nothing to push to q: no mapping needed
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles + (size_t)q * PK_IPC_HANDLE_BYTES, PK_IPC_HANDLE_BYTES);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pk_set_error("cudaIpcOpenMemHandle(halo, rank %d -> %d): %s", me, q, cudaGetErrorString(e));
+            return PK_ERR_UNSUPPORTED;
+        }
+        m->peer_recv_maps.push_back(ptr);
+        hp.peer_recv[q] = (double*)ptr;
+    }
+    PK_CUDA(cudaMalloc(&hp.seq, sizeof(unsigned long long)));
+    PK_CUDA(cudaMemset(hp.seq, 0, sizeof(unsigned long long)));
+    PK_CUDA(cudaMalloc(&hp.ticket, sizeof(unsigned int)));
+    PK_CUDA(cudaMemset(hp.ticket, 0, sizeof(unsigned int)));
+    PK_CUDA(cudaMalloc(&hp.recv_seq, sizeof(unsigned long long)));
+    PK_CUDA(cudaMemset(hp.recv_seq, 0, sizeof(unsigned long long)));
+    PK_CUDA(cudaMalloc(&hp.recv_ticket, sizeof(unsigned int)));
+    PK_CUDA(cudaMemset(hp.recv_ticket, 0, sizeof(unsigned int)));
+    m->halo_p2p = true;
+    return PK_OK;
+}
+
+void pk_mat_halo_p2p_close(pk_mat* m) {
+    for (void* q : m->peer_recv_maps) cudaIpcCloseMemHandle(q);
+    m->peer_recv_maps.clear();
+    if (m->push.seq) cudaFree(m->push.seq);
+    if (m->push.ticket) cudaFree(m->push.ticket);
+    if (m->push.recv_seq) cudaFree(m->push.recv_seq);
+    if (m->push.recv_ticket) cudaFree(m->push.recv_ticket);
+    m->push.recv_seq = nullptr;
+    m->push.recv_ticket = nullptr;
+    if (m->d_recvbuf) cudaFree(m->d_recvbuf);
+    m->d_recvbuf = nullptr;
+    m->push.seq = nullptr;
+    m->push.ticket = nullptr;
+    m->halo_p2p = false;
+}
+
 extern "C" int pk_comm_destroy(pk_ctx* ctx) {
+    if (ctx && ctx->d_p2p) {
+        cudaStreamSynchronize(ctx->stream);
+        for (void* q : ctx->peer_mbox) cudaIpcCloseMemHandle(q);
+        ctx->peer_mbox.clear();
+        cudaFree(ctx->d_p2p);
+        ctx->d_p2p = nullptr;
+    }
     if (ctx && ctx->comm) {
         if (ctx->comm->comm) g_nccl.CommDestroy(ctx->comm->comm);
         delete ctx->comm;

@@ -94,6 +94,20 @@ struct PkReduce {           // scratch for the deterministic two-stage reduction
 
 struct PkComm;  // pk_comm.cu
 
+// Peer-mapped mailboxes for the in-kernel all-reduce (pk_device.cuh: pk_grid_reduce).  One mailbox per rank, in that
+// rank's HBM, opened by every peer through CUDA IPC; layout [bank 0..1][source rank][PK_MBOX_STRIDE doubles], the
+// last slot of a row holding the sequence flag.
+constexpr int PK_MAX_RANKS = 16;
+constexpr int PK_MBOX_PAYLOAD = 6 * (PK_KMAX + 2) + 4;      // largest all-reduce: all Gram sums of a trip
+constexpr int PK_MBOX_STRIDE = PK_MBOX_PAYLOAD + 4;         // + flag (8 bytes) + padding
+constexpr size_t PK_MBOX_DOUBLES = (size_t)2 * PK_MAX_RANKS * PK_MBOX_STRIDE;
+
+struct PkP2P {
+    double* mbox[PK_MAX_RANKS];       // mbox[p]: rank p's mailbox as seen from this device
+    unsigned long long* seq;          // reductions completed so far (device counter; identical on every rank)
+    int n_ranks, rank;
+};
+
 struct pk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -106,6 +120,9 @@ struct pk_ctx {
     PkState* h_state = nullptr;      // pinned mirror for polling
     int* h_flags = nullptr;          // pinned: [slot][4]
     PkComm* comm = nullptr;
+    PkP2P* d_p2p = nullptr;          // non-null: dots are all-reduced inside the reducing kernels (NVLink mailboxes)
+    double* my_mbox = nullptr;
+    std::vector<void*> peer_mbox;    // opened IPC mappings (to close)
     int n_ranks = 1, rank = 0;
     long long launches = 0;          // kernels launched (statistics)
     long long spmvs = 0;
@@ -113,6 +130,30 @@ struct pk_ctx {
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
+    // PK_PROF_DETAIL=1: event marks between the sub-launches of a distributed operator application (stderr report)
+    bool prof_detail = false;
+    std::vector<std::pair<cudaEvent_t, int>> seg_ev;
+};
+
+// Halo exchange by direct NVLink stores (no NCCL on the data path): the owner of x pushes the entries its peers need
+// straight into their receive buffers (peer-mapped through CUDA IPC) and raises a sequence flag; the peer's boundary-row
+// SpMV waits on the flags.  Receive buffer of a rank: [32 doubles of flags: flag[bank][source]] then
+// data[bank 0..1][vector 0..1][n_halo].
+constexpr int PK_HALO_HDR = 32;
+struct PkHaloPush {
+    double* peer_recv[PK_MAX_RANKS];     // peer q's receive buffer as mapped on this device (own buffer at [me])
+    long long send_off[PK_MAX_RANKS + 1];
+    long long dst_off[PK_MAX_RANKS];     // where my entries start inside q's halo (q's recv_off[me])
+    long long peer_nhalo[PK_MAX_RANKS];
+    int send_first[PK_MAX_RANKS];
+    int send_contig[PK_MAX_RANKS];
+    const int32_t* send_idx;
+    unsigned long long* seq;             // exchanges pushed (device counter, advanced by the push kernel)
+    unsigned int* ticket;
+    unsigned long long* recv_seq;        // exchanges consumed (advanced by the boundary-row kernel; same value on all ranks)
+    unsigned int* recv_ticket;
+    int n_ranks, me;
+    unsigned int recv_mask;              // bit p set: peer p sends to me
 };
 
 enum PkMatKind : int { MAT_CSR_STREAM = 0, MAT_CSR_VECTOR = 1, MAT_DENSE = 2 };
@@ -140,6 +181,11 @@ struct pk_mat {
     std::vector<char> send_contig;               // per peer: list is a contiguous run
     std::vector<int32_t> send_first;             // per peer: first index of that run
     double* d_sendbuf = nullptr;                 // owned
+    // NVLink push path (replaces ncclSend/Recv when the peers' receive buffers are mapped)
+    bool halo_p2p = false;
+    PkHaloPush push{};
+    double* d_recvbuf = nullptr;                 // owned: [PK_HALO_HDR + 4 * n_halo]
+    std::vector<void*> peer_recv_maps;           // IPC mappings to close
     long long interior_lo = 0, interior_hi = 0;
     long long ld = 0;
 };

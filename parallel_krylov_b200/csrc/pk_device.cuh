@@ -15,6 +15,9 @@ struct PkRedArgs {
     int block_off;          // this launch's partials start at this block slot
     int nb_total;           // slots the final reduction covers (0: gridDim.x)
     int store_only;         // 1: just store the partials (a later launch on the same stream finishes)
+    // multi-GPU all-reduce fused into this kernel's last block (NVLink peer stores into per-rank mailboxes)
+    const PkP2P* p2p;       // nullptr: single GPU, or NCCL path (defer = 1)
+    int ar_n;               // doubles to all-reduce once the local sums are published (0: local publish only)
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -238,10 +241,56 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
         if (lane == 0) tot[j] = v;
     }
     __syncthreads();
+    double* dst = (ra.g_off >= 0) ? (ra.st->gram + ra.g_off) : ra.st->red;
     if (threadIdx.x == 0) {
         *ra.ticket = 0u;
-        double* dst = (ra.g_off >= 0) ? (ra.st->gram + ra.g_off) : ra.st->red;
         for (int j = 0; j < NS; ++j) dst[j] = tot[j];
-        if (!ra.defer) pk_epilogue<GRAM>(ra.epi, ra.st);
     }
+    if (ra.p2p != nullptr && ra.ar_n > 0) {
+        // ---- all-reduce over NVLink, inside this kernel --------------------------------------------------------------
+        // Every rank's last block stores its local sums into every rank's mailbox (peer-mapped memory, plain stores
+        // through NVSwitch), publishes a sequence flag, waits for the P flags addressed to it, and adds the P
+        // contributions in RANK ORDER — so all ranks obtain bit-identical sums and take identical decisions.  Two
+        // mailbox banks (sequence parity) suffice: a rank can run at most one reduction ahead of a peer.
+        __syncthreads();
+        const PkP2P* pp = ra.p2p;
+        const int P = pp->n_ranks, me = pp->rank;
+        double* buf = (ra.g_off >= 0) ? ra.st->gram : ra.st->red;   // Gram: the whole gram[] (all windows) is reduced
+        const int n = ra.ar_n;
+        const unsigned long long seq = *pp->seq + 1ull;
+        const int bank = (int)(seq & 1ull);
+        for (int t = threadIdx.x; t < n * P; t += BLOCK) {
+            const int p = t / n, j = t - p * n;
+            pp->mbox[p][((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + j] = buf[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < P) {
+            volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
+                pp->mbox[threadIdx.x] + ((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
+            *f = seq;
+            volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(
+                pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + threadIdx.x)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
+            long long spins = 0;
+            while (*mine != seq) {
+                if (++spins > (1ll << 31)) {          // a peer never arrived: stop the solve instead of hanging
+                    ra.st->done = 1;
+                    ra.st->converged = 0;
+                    ra.st->guard = -1;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += BLOCK) {
+            double v = 0.0;
+            for (int p = 0; p < P; ++p)
+                v += __ldcv(pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + p)) * PK_MBOX_STRIDE + j);
+            buf[j] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *pp->seq = seq;
+    }
+    if (threadIdx.x == 0 && !ra.defer) pk_epilogue<GRAM>(ra.epi, ra.st);
 }

@@ -207,11 +207,19 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
     ra.max_blocks = ctx->red.max_blocks;
     ra.st = ctx->d_state;
     ra.epi = epi;
-    ra.defer = ctx->n_ranks > 1 ? 1 : 0;
+    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p) ? 1 : 0;
     ra.g_off = g_off;
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
+    ra.p2p = ctx->d_p2p;
+    ra.ar_n = 0;          // set by the launcher: number of sums this kernel all-reduces
+    return ra;
+}
+
+inline PkRedArgs red_args_n(pk_ctx* ctx, int epi, int nsums) {
+    PkRedArgs ra = red_args(ctx, epi);
+    ra.ar_n = (epi == EPI_KS_STEP) ? 0 : nsums;
     return ra;
 }
 
@@ -270,7 +278,7 @@ int pk_launch_set_k(pk_ctx* ctx, int k) {
 // After a reducing kernel: single GPU -> nothing to do (the last block already ran the epilogue);
 // multi GPU -> all-reduce the published sums over NVLink, then run the scalar engine.
 int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done) {
-    if (ctx->n_ranks <= 1) return PK_OK;
+    if (ctx->n_ranks <= 1 || ctx->d_p2p) return PK_OK;   // single GPU, or all-reduced inside the kernel
     double* buf = (g_off >= 0) ? (ctx->d_state->gram + g_off) : ctx->d_state->red;
     PK_CHECK(pk_comm_allreduce(ctx, buf, nsums, ctx->stream));
     if (epi != EPI_NONE && epi != EPI_GRAM_PART && epi != EPI_KS_STEP) return pk_launch_scalar(ctx, epi, ignore_done);
@@ -278,19 +286,19 @@ int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done
 }
 
 int pk_launch_dot(pk_ctx* ctx, long long n, const double* u, const double* v, int epi, int ignore_done) {
-    k_dot<<<ew_grid(ctx, k_dot, n), EW_BLOCK, 0, ctx->stream>>>(n, u, v, red_args(ctx, epi), ignore_done);
+    k_dot<<<ew_grid(ctx, k_dot, n), EW_BLOCK, 0, ctx->stream>>>(n, u, v, red_args_n(ctx, epi, 1), ignore_done);
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, ignore_done);
 }
 
 int pk_launch_resid_init(pk_ctx* ctx, long long n, const double* b, const double* v, double* r, double* p, int epi) {
-    k_resid_init<<<ew_grid(ctx, k_resid_init, n), EW_BLOCK, 0, ctx->stream>>>(n, b, v, r, p, red_args(ctx, epi));
+    k_resid_init<<<ew_grid(ctx, k_resid_init, n), EW_BLOCK, 0, ctx->stream>>>(n, b, v, r, p, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v) {
-    k_cg_xr<<<ew_grid(ctx, k_cg_xr, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args(ctx, EPI_CG_BETA));
+    k_cg_xr<<<ew_grid(ctx, k_cg_xr, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args_n(ctx, EPI_CG_BETA, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, EPI_CG_BETA, -1, 0);
 }
@@ -303,27 +311,27 @@ int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r) {
 
 int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
                         int epi) {
-    k_mrr_first<<<ew_grid(ctx, k_mrr_first, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, r, x, y, z, red_args(ctx, epi));
+    k_mrr_first<<<ew_grid(ctx, k_mrr_first, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, r, x, y, z, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r) {
-    k_mrr_s<<<ew_grid(ctx, k_mrr_s, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args(ctx, EPI_MRR_ZETA));
+    k_mrr_s<<<ew_grid(ctx, k_mrr_s, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args_n(ctx, EPI_MRR_ZETA, 2));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
 }
 
 int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
                          int cj, int epi) {
-    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args(ctx, epi));
+    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
 int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
                           int epi) {
-    k_kscg_update<<<ew_grid(ctx, k_kscg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args(ctx, epi));
+    k_kscg_update<<<ew_grid(ctx, k_kscg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
@@ -331,27 +339,29 @@ int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, doub
 namespace {
 template <int W, int MODE>
 int gram_window(pk_ctx* ctx, long long n, long long ld, const double* U, int nu, const double* V, int nv, int j0,
-                int epi) {
+                int epi, int ar_n) {
     int grid = ew_grid(ctx, k_gram<W, MODE>, n, 1);   // register-heavy (6W accumulators): occupancy decides the grid
-    k_gram<W, MODE><<<grid, EW_BLOCK, 0, ctx->stream>>>(n, ld, U, nu, V, nv, j0, red_args(ctx, epi, 6 * j0));
+    PkRedArgs ra = red_args(ctx, epi, 6 * j0);
+    ra.ar_n = ar_n;
+    k_gram<W, MODE><<<grid, EW_BLOCK, 0, ctx->stream>>>(n, ld, U, nu, V, nv, j0, ra);
     PK_LAUNCH_CHECK();
     return PK_OK;
 }
 
 template <int MODE>
 int gram_dispatch(pk_ctx* ctx, int w, long long n, long long ld, const double* U, int nu, const double* V, int nv,
-                  int j0, int epi) {
+                  int j0, int epi, int ar_n) {
     switch (w) {
-        case 1: return gram_window<1, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 2: return gram_window<2, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 3: return gram_window<3, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 4: return gram_window<4, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 5: return gram_window<5, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 6: return gram_window<6, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 7: return gram_window<7, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 8: return gram_window<8, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 9: return gram_window<9, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
-        case 10: return gram_window<10, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi);
+        case 1: return gram_window<1, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 2: return gram_window<2, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 3: return gram_window<3, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 4: return gram_window<4, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 5: return gram_window<5, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 6: return gram_window<6, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 7: return gram_window<7, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 8: return gram_window<8, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 9: return gram_window<9, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
+        case 10: return gram_window<10, MODE>(ctx, n, ld, U, nu, V, nv, j0, epi, ar_n);
         default: pk_set_error("gram window %d unsupported", w); return PK_ERR_ARG;
     }
 }
@@ -372,11 +382,12 @@ int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const doubl
         int w = njj - j0 < WMAX ? njj - j0 : WMAX;
         bool last = (j0 + w >= njj);
         int epi = last ? final_epi : EPI_GRAM_PART;
-        if (mode == 0) PK_CHECK((gram_dispatch<0>(ctx, w, n, ld, U, nu, V, nv, j0, epi)));
-        else PK_CHECK((gram_dispatch<1>(ctx, w, n, ld, U, nu, V, nv, j0, epi)));
+        const int ar_n = last ? 6 * njj : 0;
+        if (mode == 0) PK_CHECK((gram_dispatch<0>(ctx, w, n, ld, U, nu, V, nv, j0, epi, ar_n)));
+        else PK_CHECK((gram_dispatch<1>(ctx, w, n, ld, U, nu, V, nv, j0, epi, ar_n)));
         j0 += w;
     }
-    if (ctx->n_ranks > 1) {
+    if (ctx->n_ranks > 1 && !ctx->d_p2p) {
         PK_CHECK(pk_comm_allreduce(ctx, ctx->d_state->gram, 6LL * njj, ctx->stream));
         if (final_epi != EPI_NONE) PK_CHECK(pk_launch_scalar(ctx, final_epi, 0));
     }

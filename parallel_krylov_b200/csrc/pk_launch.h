@@ -36,4 +36,5 @@ int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int ti
 int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s);
 int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s);
 int pk_comm_halo_start(pk_ctx* ctx, pk_mat* mat, double* x, double* x1);   // pack + send/recv on the side stream
-int pk_comm_halo_wait(pk_ctx* ctx);                                        // main stream waits for the exchange
+int pk_comm_halo_wait(pk_ctx* ctx);
+void pk_mat_halo_p2p_close(pk_mat* m);                                        // main stream waits for the exchange

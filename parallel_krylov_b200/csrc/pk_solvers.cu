@@ -109,6 +109,7 @@ extern "C" int pk_prof_begin(pk_ctx* c, int max_launches) {
     }
     c->prof_used = 0;
     c->prof_on = true;
+    c->prof_detail = getenv("PK_PROF_DETAIL") != nullptr;
     return PK_OK;
 }
 
@@ -120,6 +121,22 @@ extern "C" int pk_prof_end(pk_ctx* c, double* total_ms, int64_t* n_launches) {
         float ms = 0.f;
         PK_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
         tot += ms;
+    }
+    if (c->prof_detail && !c->seg_ev.empty()) {
+        double seg[4] = {0, 0, 0, 0};
+        long long cnt[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i + 1 < c->seg_ev.size(); ++i) {
+            const int t0 = c->seg_ev[i].second, t1 = c->seg_ev[i + 1].second;
+            if (t1 == t0 + 1) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, c->seg_ev[i].first, c->seg_ev[i + 1].first) == cudaSuccess) { seg[t0] += ms; cnt[t0]++; }
+            }
+        }
+        fprintf(stderr, "[pk prof rank %d] push %.1f us, interior %.1f us, boundary %.1f us (avg over %lld applications)\n",
+                c->rank, cnt[0] ? 1e3 * seg[0] / cnt[0] : 0.0, cnt[1] ? 1e3 * seg[1] / cnt[1] : 0.0,
+                cnt[2] ? 1e3 * seg[2] / cnt[2] : 0.0, cnt[0]);
+        for (auto& pr : c->seg_ev) cudaEventDestroy(pr.first);
+        c->seg_ev.clear();
     }
     if (total_ms) *total_ms = tot;
     if (n_launches) *n_launches = (int64_t)(c->prof_used / 2);
@@ -192,6 +209,7 @@ extern "C" int pk_mat_dense(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n
 extern "C" int pk_mat_destroy(pk_mat* m) {
     if (!m) return PK_OK;
     if (m->d_sendbuf) cudaFree(m->d_sendbuf);
+    pk_mat_halo_p2p_close(m);
     delete m;
     return PK_OK;
 }

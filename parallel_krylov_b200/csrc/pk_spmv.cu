@@ -30,6 +30,14 @@ struct SpmvArgs {
     const double* w;        // fused dots against this vector (nullable)
     int w_is_x;             // w == x0 (CG's p.Ap): take w[row] from the diagonal gather instead of loading it again
     long long row_lo, row_hi;
+    long long row_lo2, row_hi2;   // optional second row range processed by the same launch (boundary rows above/below)
+    // halo received by NVLink push: columns >= n_own read from the receive buffer after waiting for the peers' flags
+    const double* hrecv;          // receive buffer base (nullptr: columns index x directly)
+    unsigned long long* hseq;     // exchanges consumed so far (this kernel waits for hseq+1 and advances it)
+    unsigned int* hticket;
+    long long n_own, n_halo;
+    unsigned int recv_mask;
+    int n_ranks;
     long long nnz_total;
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
@@ -195,7 +203,7 @@ struct TileMeta {
     int pad;
 };
 
-template <int NV, int BLOCK, int STAGES>
+template <int NV, int BLOCK, int STAGES, bool HALO>
 __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     if (pk_done(ra.st)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -209,8 +217,14 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc[3] = {0.0, 0.0, 0.0};
-    const long long n_rows = a.row_hi - a.row_lo;
-    const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
+    // tile index space: tiles of [row_lo,row_hi) followed by tiles of [row_lo2,row_hi2)
+    const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
+    const long long tiles_b = (HALO && a.row_hi2 > a.row_lo2) ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
+    const long long n_tiles = tiles_a + tiles_b;
+    auto tile_rows = [&](long long tile, long long& r0, long long& rend) {
+        if (!HALO || tile < tiles_a) { r0 = a.row_lo + tile * BLOCK; rend = a.row_hi; }
+        else { r0 = a.row_lo2 + (tile - tiles_a) * BLOCK; rend = a.row_hi2; }
+    };
     const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == 0) {
@@ -223,8 +237,9 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     auto issue = [&](long long i, int nb, int ne) {
         const int s = (int)(i % STAGES);
         const long long tile = blockIdx.x + i * (long long)gridDim.x;
-        const long long r0 = a.row_lo + tile * BLOCK;
-        const int nr = (int)((a.row_hi - r0) < BLOCK ? (a.row_hi - r0) : BLOCK);
+        long long r0, rend;
+        tile_rows(tile, r0, rend);
+        const int nr = (int)((rend - r0) < BLOCK ? (rend - r0) : BLOCK);
         const int q0 = nb & ~3;
         const int cnt = (ne - q0 + 3) & ~3;
         const long long ra0 = r0 & ~3LL;
@@ -246,8 +261,9 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     };
     auto endpoints = [&](long long i, int& nb, int& ne) {
         const long long tile = blockIdx.x + i * (long long)gridDim.x;
-        const long long r0 = a.row_lo + tile * BLOCK;
-        const long long r1 = (r0 + BLOCK < a.row_hi) ? r0 + BLOCK : a.row_hi;
+        long long r0, rend;
+        tile_rows(tile, r0, rend);
+        const long long r1 = (r0 + BLOCK < rend) ? r0 + BLOCK : rend;
         nb = __ldg(a.rowptr + r0);
         ne = __ldg(a.rowptr + r1);
     };
@@ -261,6 +277,30 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         if (STAGES - 1 < my_tiles) endpoints(STAGES - 1, nb, ne);
     }
 
+    // Halo pushed by the peers over NVLink: wait (once per block) for the flags of this exchange; the bulk copies of
+    // the first tiles are already in flight.  Halo entries are then read from the receive buffer, bypassing L1.
+    const double* h0 = nullptr;
+    const double* h1 = nullptr;
+    unsigned long long hseq_next = 0;
+    if (HALO) {
+        const unsigned long long seq = *a.hseq + 1ull;
+        hseq_next = seq;
+        const int bank = (int)(seq & 1ull);
+        if (tid < a.n_ranks && ((a.recv_mask >> tid) & 1u)) {
+            const volatile unsigned long long* f =
+                reinterpret_cast<const volatile unsigned long long*>(a.hrecv) + bank * PK_MAX_RANKS + tid;
+            long long spins = 0;
+            while (*f != seq) {
+                if (++spins > (1ll << 31)) { ra.st->done = 1; ra.st->converged = 0; ra.st->guard = -2; break; }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        h0 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 0) * a.n_halo - a.n_own;   // indexed by the column itself
+        h1 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 1) * a.n_halo - a.n_own;
+    }
+    const int n_own = (int)a.n_own;
+
     for (long long i = 0; i < my_tiles; ++i) {
         const int s = (int)(i % STAGES);
         if (tid == 0) {
@@ -272,8 +312,9 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         }
         mbar_wait(&full[s], (unsigned)((i / STAGES) & 1));
         const long long tile = blockIdx.x + i * (long long)gridDim.x;
-        const long long r0 = a.row_lo + tile * BLOCK;
-        const int nr = (int)((a.row_hi - r0) < BLOCK ? (a.row_hi - r0) : BLOCK);
+        long long r0, rend;
+        tile_rows(tile, r0, rend);
+        const int nr = (int)((rend - r0) < BLOCK ? (rend - r0) : BLOCK);
         double* sval = st_val(s);
         int* scol = st_col(s);
         int* rp = st_rp(s);
@@ -310,8 +351,17 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                         const bool ok = j + u < se;
                         const int c = ok ? scol[j + u] : 0;
                         vv[u] = ok ? sval[j + u] : 0.0;
-                        xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
-                        if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
+                        if (!HALO) {
+                            xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
+                            if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
+                        } else {   // boundary rows: halo columns live in the receive buffer (branch-free select, L2 loads)
+                            const double* s0 = c < n_own ? a.x0 : h0;
+                            xa[u] = ok ? __ldcg(s0 + c) : 0.0;
+                            if (NV == 2) {
+                                const double* s1 = c < n_own ? a.x1 : h1;
+                                xb[u] = ok ? __ldcg(s1 + c) : 0.0;
+                            }
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
@@ -336,8 +386,13 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                 for (int q = sb + lane; q < se; q += 32) {
                     const int c = a.col[q];
                     const double v = a.val[q];
-                    sum0 += v * __ldg(a.x0 + c);
-                    if (NV == 2) sum1 += v * __ldg(a.x1 + c);
+                    if (!HALO) {
+                        sum0 += v * __ldg(a.x0 + c);
+                        if (NV == 2) sum1 += v * __ldg(a.x1 + c);
+                    } else {
+                        sum0 += v * __ldcg((c < n_own ? a.x0 : h0) + c);
+                        if (NV == 2) sum1 += v * __ldcg((c < n_own ? a.x1 : h1) + c);
+                    }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -359,7 +414,75 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         }
         __syncthreads();   // everyone is done with stage s: thread 0 may refill it next iteration
     }
+    if (HALO) {
+        // the last block to finish advances the consumed-exchange counter (every block read it at its start)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(a.hticket, 1u) == gridDim.x - 1) {
+                *a.hticket = 0u;
+                *a.hseq = hseq_next;
+            }
+        }
+    }
     if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
+}
+
+// Owner-side halo push: store the entries each peer needs straight into that peer's receive buffer over NVLink, fence,
+// then (last block) raise the sequence flags.  Replaces pack kernel + ncclSend/ncclRecv + the side stream.
+__global__ void __launch_bounds__(256) k_halo_push(PkHaloPush hp, const double* __restrict__ x0,
+                                                   const double* __restrict__ x1, const PkState* st) {
+    if (pk_done(st)) return;
+    const unsigned long long seq = *hp.seq + 1ull;
+    const int bank = (int)(seq & 1ull);
+    const long long total = hp.send_off[hp.n_ranks];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 4;                       // loads of U entries in flight before the remote stores
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        double v0[U], v1[U];
+        double* dst[U];
+        long long nh[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            dst[u] = nullptr;
+            if (i < total) {
+                int q = 0;
+                while (i >= hp.send_off[q + 1]) ++q;
+                const long long k = i - hp.send_off[q];
+                const long long src = hp.send_contig[q] ? (long long)hp.send_first[q] + k : (long long)hp.send_idx[i];
+                nh[u] = hp.peer_nhalo[q];
+                dst[u] = hp.peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh[u] + hp.dst_off[q] + k;
+                v0[u] = x0[src];
+                if (x1) v1[u] = x1[src];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (dst[u]) {
+                dst[u][0] = v0[u];
+                if (x1) dst[u][nh[u]] = v1[u];
+            }
+        }
+    }
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();      // cumulative: orders the whole block's remote stores (bar.sync above) before the ticket
+        is_last = (atomicAdd(hp.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (threadIdx.x < hp.n_ranks && hp.send_off[threadIdx.x + 1] > hp.send_off[threadIdx.x]) {
+        volatile unsigned long long* f =
+            reinterpret_cast<volatile unsigned long long*>(hp.peer_recv[threadIdx.x]) + bank * PK_MAX_RANKS + hp.me;
+        *f = seq;
+    }
+    if (threadIdx.x == 0) {
+        *hp.ticket = 0u;
+        *hp.seq = seq;
+    }
 }
 
 // Dense row-major block: warp per row.
@@ -482,16 +605,17 @@ int launch_plain_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedA
 }
 
 // ---- TMA variant launcher ------------------------------------------------------------------------------------------
-template <int NV, int BLOCK, int STAGES>
+template <int NV, int BLOCK, int STAGES, bool HALO>
 int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int grid_cap, int mode) {
     const size_t stage_bytes = (((size_t)a.cap * 12 + (BLOCK + 8) * 4) + 127) / 128 * 128;
     const size_t smem = stage_bytes * STAGES;
     const long long n_rows = a.row_hi - a.row_lo;
-    if (n_rows <= 0) { *grid_io = 0; return PK_OK; }
-    const long long n_tiles = (n_rows + BLOCK - 1) / BLOCK;
+    const long long n_rows2 = a.row_hi2 > a.row_lo2 ? a.row_hi2 - a.row_lo2 : 0;
+    if (n_rows <= 0 && n_rows2 <= 0) { *grid_io = 0; return PK_OK; }
+    const long long n_tiles = (n_rows > 0 ? (n_rows + BLOCK - 1) / BLOCK : 0) + (n_rows2 + BLOCK - 1) / BLOCK;
     int grid = *grid_io;
     if (mode != 2) {
-        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES>, BLOCK, smem);
+        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO>, BLOCK, smem);
         long long g = (long long)ctx->sm_count * per_sm;
         if (g > n_tiles) g = n_tiles;
         if (g > grid_cap) g = grid_cap;
@@ -499,9 +623,9 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
         *grid_io = grid;
         if (mode == 1) return PK_OK;
     } else {
-        pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES>, BLOCK, smem);   // sets the smem attribute
+        pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO>, BLOCK, smem);   // sets the smem attribute
     }
-    k_spmv_tma<NV, BLOCK, STAGES><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
+    k_spmv_tma<NV, BLOCK, STAGES, HALO><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         pk_set_error("spmv(tma) launch (grid %d, smem %zu): %s", grid, smem, cudaGetErrorString(e));
@@ -513,10 +637,11 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
 
 template <int NV, int BLOCK>
 int launch_tma_stages(pk_ctx* ctx, int stages, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
+    if (a.hrecv != nullptr) return launch_tma<NV, BLOCK, 2, true>(ctx, a, ra, grid_io, cap, mode);
     switch (stages) {
-        case 2: return launch_tma<NV, BLOCK, 2>(ctx, a, ra, grid_io, cap, mode);
-        case 4: return launch_tma<NV, BLOCK, 4>(ctx, a, ra, grid_io, cap, mode);
-        default: return launch_tma<NV, BLOCK, 3>(ctx, a, ra, grid_io, cap, mode);
+        case 3: return launch_tma<NV, BLOCK, 3, false>(ctx, a, ra, grid_io, cap, mode);
+        case 4: return launch_tma<NV, BLOCK, 4, false>(ctx, a, ra, grid_io, cap, mode);
+        default: return launch_tma<NV, BLOCK, 2, false>(ctx, a, ra, grid_io, cap, mode);
     }
 }
 
@@ -590,6 +715,14 @@ int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int ti
 
 static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots);
 
+static void seg_mark(pk_ctx* ctx, int tag) {
+    if (!ctx->prof_detail || !ctx->prof_on || ctx->seg_ev.size() > 60000) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    ctx->seg_ev.push_back({e, tag});
+}
+
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots) {
     bool prof = false;
     if (ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size()) {
@@ -614,7 +747,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.max_blocks = ctx->red.max_blocks;
     ra.st = ctx->d_state;
     ra.epi = dots.epi;
-    ra.defer = ctx->n_ranks > 1 ? 1 : 0;
+    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p) ? 1 : 0;
+    ra.p2p = ctx->d_p2p;
+    ra.ar_n = dots.w ? 3 : 0;
     ra.g_off = -1;
     ra.block_off = 0;
     ra.nb_total = 0;
@@ -642,6 +777,8 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.w_is_x = (dots.w == x) ? 1 : 0;
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
+    a.row_lo2 = a.row_hi2 = 0;
+    a.hrecv = nullptr; a.hseq = nullptr; a.hticket = nullptr; a.n_own = m->n_rows; a.n_halo = m->n_halo; a.recv_mask = 0; a.n_ranks = ctx->n_ranks;
     a.cap = m->tile_cap;
     a.reduce = dots.w ? 1 : 0;
     int grid = 0;
@@ -649,6 +786,43 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     if (!m->distributed || m->n_halo == 0) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
+    } else if (m->halo_p2p && m->use_tma) {
+        // NVLink push path, one stream: [push my boundary entries into the peers' receive buffers + flags] ->
+        // [interior rows] -> [boundary rows: wait for the peers' flags, read halo columns from the receive buffer].
+        seg_mark(ctx, 0);
+        {
+            // push on the side stream: it overlaps the interior rows; x must be complete first (event), and it must not
+            // be overwritten before the push has read it (the main stream waits for ev_b before the boundary rows)
+            const long long total = m->push.send_off[ctx->n_ranks];
+            int pg = (int)((total + 255) / 256);
+            if (pg > ctx->sm_count * 4) pg = ctx->sm_count * 4;
+            if (pg < 1) pg = 1;
+            PK_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+            PK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_a, 0));
+            k_halo_push<<<pg, 256, 0, ctx->side>>>(m->push, x, x1, ctx->d_state);
+            PK_CUDA(cudaGetLastError());
+            PK_CUDA(cudaEventRecord(ctx->ev_b, ctx->side));
+            ctx->launches++;
+        }
+        seg_mark(ctx, 1);
+        const long long lo = m->interior_lo, hi = m->interior_hi;
+        const int cap_each = ctx->red.max_blocks / 2;
+        int g_int = 0, g_bnd = 0;
+        SpmvArgs ai = a, ab = a;
+        ai.row_lo = lo; ai.row_hi = hi;
+        ab.row_lo = 0; ab.row_hi = lo; ab.row_lo2 = hi; ab.row_hi2 = m->n_rows;
+        ab.hrecv = m->d_recvbuf; ab.hseq = m->push.recv_seq; ab.hticket = m->push.recv_ticket;
+        ab.recv_mask = m->push.recv_mask;
+        PK_CHECK(launch_stream_any(ctx, m, two, ai, ra, &g_int, cap_each, 1));
+        PK_CHECK(launch_stream_any(ctx, m, two, ab, ra, &g_bnd, cap_each, 1));
+        PkRedArgs r1 = ra, r2 = ra;
+        r1.block_off = 0; r1.nb_total = g_int + g_bnd; r1.store_only = (g_bnd > 0) ? 1 : 0;
+        r2.block_off = g_int; r2.nb_total = g_int + g_bnd; r2.store_only = 0;
+        if (g_int > 0) PK_CHECK(launch_stream_any(ctx, m, two, ai, r1, &g_int, cap_each, 2));
+        seg_mark(ctx, 2);
+        PK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+        if (g_bnd > 0) PK_CHECK(launch_stream_any(ctx, m, two, ab, r2, &g_bnd, cap_each, 2));
+        seg_mark(ctx, 3);
     } else {
         // Interior rows (no halo column) run while the halo of x is in flight on the side stream; the boundary
         // rows follow the exchange.  All launches store partials into disjoint block slots of ONE reduction,

@@ -13,6 +13,7 @@ on CPU tensors over ``gloo`` (tests/test_dist_gloo.py) and on CUDA tensors over 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -20,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from .._core import Context, Operator, _ptr
-from .._lib import PkError, check
+from .._lib import PK_IPC_HANDLE_BYTES, PkError, check
 
 
 def _all_gather_int(value: int, group, device) -> list:
@@ -166,7 +167,33 @@ class DistOperator(Operator):
                                               ro.ctypes.data_as(C.c_void_p), _ptr(send_idx_d),
                                               C.c_void_p(send_idx_h.data_ptr()), plan["interior"][0],
                                               plan["interior"][1]), "pk_mat_set_halo")
+                if ctx.fused_allreduce and os.environ.get("PK_HALO", "nccl") == "p2p":
+                    op._open_halo_push(group, world, rank, plan)
         return op
+
+    def _open_halo_push(self, group, world, rank, plan):
+        """Map the peers' halo receive buffers (CUDA IPC) so that the halo is exchanged by direct NVLink stores from
+        inside libpkrylov instead of ncclSend/ncclRecv."""
+        ctx = self.ctx
+        dev = ctx.torch_device
+        hb = C.create_string_buffer(PK_IPC_HANDLE_BYTES)
+        check(ctx.lib.pk_mat_halo_p2p_handle(self.handle, hb), "pk_mat_halo_p2p_handle")
+        cdev = _comm_device(group)
+        mine = torch.tensor(list(hb.raw), dtype=torch.uint8, device=cdev)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        ro = torch.tensor(plan["recv_off"], dtype=torch.int64, device=cdev)
+        allro = [torch.zeros_like(ro) for _ in range(world)]
+        dist.all_gather(allro, ro, group=group)
+        dst_off = np.asarray([int(allro[q][rank].item()) for q in range(world)], dtype=np.int64)
+        nhalo = np.asarray([int(allro[q][world].item()) for q in range(world)], dtype=np.int64)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        rc = ctx.lib.pk_mat_halo_p2p_open(self.handle, raw, dst_off.ctypes.data_as(C.c_void_p),
+                                          nhalo.ctypes.data_as(C.c_void_p))
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=cdev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            raise PkError("peer mapping of the halo receive buffers failed on some rank; set PK_HALO=nccl")
 
     @classmethod
     def from_local_dense(cls, local_a: torch.Tensor, group=None, ctx: Optional[Context] = None) -> "DistOperator":

@@ -20,8 +20,13 @@ elif which.startswith("p2d"):
 else:
     n = 1 << 25 if which == "band32m" else 1 << 22
     rowptr, col, val, n = dp.banded_csr(n, 13, 0)
+if os.environ.get("KB_HALF"):          # first half of the rows only (what one of two ranks owns)
+    h = n // 2
+    nz = int(rowptr[h].item())
+    rowptr, col, val = rowptr[: h + 1].clone(), col[:nz].clone(), val[:nz].clone()
 nnz = val.numel()
 op = Operator.from_csr_tensors(rowptr, col, val, n, ctx)
+n_rows = rowptr.numel() - 1
 ld = op.ld
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 print(f"{which}: n={n} nnz={nnz} {op.kernel_info()} peak={PEAK}")
@@ -41,7 +46,7 @@ def timeit(fn, nbytes, label):
     print(f"{label:34s} {ms*1e3:9.1f} us  {gbs:8.1f} GB/s  {100*gbs/PEAK:5.1f}% of measured peak")
     return ms
 
-b_spmv = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
+b_spmv = 12.0 * nnz + 4.0 * (n_rows + 1) + 16.0 * n_rows
 N0 = C.c_void_p(0)
 timeit(lambda: _lib.check(lib.pk_spmv(ctx.handle, op.handle, _ptr(vecs[0]), _ptr(y0), N0, N0, N0, N0)), b_spmv, "spmv")
 timeit(lambda: _lib.check(lib.pk_spmv(ctx.handle, op.handle, _ptr(vecs[0]), _ptr(y0), N0, N0, _ptr(vecs[0]), _ptr(sums))), b_spmv, "spmv + fused dots (w = x)")
