@@ -5,6 +5,7 @@
 #include "pk_launch.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <map>
 
@@ -180,6 +181,96 @@ __global__ void __launch_bounds__(EW_BLOCK) k_gram(long long n, long long ld, co
     pk_grid_reduce<6 * W, EW_BLOCK, true>(acc, ra);
 }
 
+// ---- Gram window, TMA-pipelined: the (up to 2W+2) basis rows of a tile of T elements are brought into shared memory by
+// 1-D bulk copies (ring of STAGES buffers, mbarrier per stage) while the previous tile is reduced, so HBM stays busy
+// although the 6W register accumulators allow only one or two blocks per SM.  Same sums, same per-thread order of
+// additions as k_gram (thread t owns elements t, t+T*grid, ...), hence bit-identical results for equal grids.
+template <int W, int MODE, int STAGES>
+__global__ void __launch_bounds__(EW_BLOCK) k_gram_tma(long long n, long long ld, const double* __restrict__ U, int nu,
+                                                       const double* __restrict__ V, int nv, int j0, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    constexpr int T = EW_BLOCK;                     // elements per tile (one per thread)
+    constexpr int ROWS = 2 * (W + 1);
+    extern __shared__ __align__(128) unsigned char gsm_raw[];
+    double* gsm = reinterpret_cast<double*>(gsm_raw);            // [STAGES][ROWS][T]
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    const int tid = threadIdx.x;
+    double acc[6 * W];
+#pragma unroll
+    for (int t = 0; t < 6 * W; ++t) acc[t] = 0.0;
+    const long long n_full = n / T;                 // tiles that can be bulk-copied; the tail is read directly
+    const long long my_tiles = n_full > blockIdx.x ? (n_full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int n_rows_present = 0;
+#pragma unroll
+    for (int t = 0; t <= W; ++t) n_rows_present += (j0 + t < nu) + (j0 + t < nv);
+    // warp 0 issues the copies, one basis row per lane (a single thread issuing 2W+2 copies per tile serialises the
+    // block); lane r < ROWS owns row r: even r = U[j0 + r/2], odd r = V[j0 + r/2]
+    const double* my_row = nullptr;
+    if (tid < ROWS) {
+        const int t = tid >> 1;
+        if ((tid & 1) == 0) { if (j0 + t < nu) my_row = U + (long long)(j0 + t) * ld; }
+        else { if (j0 + t < nv) my_row = V + (long long)(j0 + t) * ld; }
+    }
+    auto issue = [&](long long i) {     // called by all lanes of warp 0
+        const int s = (int)(i % STAGES);
+        const long long e0 = (blockIdx.x + i * (long long)gridDim.x) * T;
+        if (tid == 0) mbar_expect_tx(&full[s], (unsigned)(n_rows_present * T * sizeof(double)));
+        __syncwarp();
+        if (my_row) bulk_g2s(gsm + ((size_t)s * ROWS + tid) * T, my_row + e0, T * sizeof(double), &full[s]);
+    };
+    if (tid < 32)
+        for (long long i = 0; i < STAGES - 1 && i < my_tiles; ++i) issue(i);
+    for (long long i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i % STAGES);
+        if (tid < 32 && i + STAGES - 1 < my_tiles) issue(i + STAGES - 1);
+        mbar_wait(&full[s], (unsigned)((i / STAGES) & 1));
+        const double* src = gsm + (size_t)s * ROWS * T + tid;
+        double u[W + 1], v[W + 1];
+#pragma unroll
+        for (int t = 0; t <= W; ++t) {
+            u[t] = (j0 + t < nu) ? src[(size_t)(2 * t) * T] : 0.0;
+            v[t] = (j0 + t < nv) ? src[(size_t)(2 * t + 1) * T] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            acc[6 * t + 0] += u[t] * u[t];
+            acc[6 * t + 1] += u[t] * u[t + 1];
+            acc[6 * t + 2] += u[t] * v[t];
+            acc[6 * t + 3] += (MODE == 0) ? (v[t] * u[t + 1]) : (u[t] * v[t + 1]);
+            acc[6 * t + 4] += v[t] * v[t];
+            acc[6 * t + 5] += v[t] * v[t + 1];
+        }
+        __syncthreads();      // stage s may be refilled by the next iteration's issue
+    }
+    // tail elements (n % T) by block 0, read directly
+    if (blockIdx.x == 0) {
+        const long long i = n_full * T + tid;
+        if (i < n) {
+            double u[W + 1], v[W + 1];
+#pragma unroll
+            for (int t = 0; t <= W; ++t) {
+                u[t] = (j0 + t < nu) ? U[(long long)(j0 + t) * ld + i] : 0.0;
+                v[t] = (j0 + t < nv) ? V[(long long)(j0 + t) * ld + i] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < W; ++t) {
+                acc[6 * t + 0] += u[t] * u[t];
+                acc[6 * t + 1] += u[t] * u[t + 1];
+                acc[6 * t + 2] += u[t] * v[t];
+                acc[6 * t + 3] += (MODE == 0) ? (v[t] * u[t + 1]) : (u[t] * v[t + 1]);
+                acc[6 * t + 4] += v[t] * v[t];
+                acc[6 * t + 5] += v[t] * v[t + 1];
+            }
+        }
+    }
+    pk_grid_reduce<6 * W, EW_BLOCK, true>(acc, ra);
+}
+
 __global__ void k_scalar(PkState* st, int epi, int ignore_done) {
     if (!ignore_done && pk_done(st)) return;
     pk_epilogue<true>(epi, st);
@@ -340,9 +431,28 @@ namespace {
 template <int W, int MODE>
 int gram_window(pk_ctx* ctx, long long n, long long ld, const double* U, int nu, const double* V, int nv, int j0,
                 int epi, int ar_n) {
-    int grid = ew_grid(ctx, k_gram<W, MODE>, n, 1);   // register-heavy (6W accumulators): occupancy decides the grid
     PkRedArgs ra = red_args(ctx, epi, 6 * j0);
     ra.ar_n = ar_n;
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char* e = getenv("PK_GRAM");
+        use_tma = !(e && strcmp(e, "plain") == 0);
+    }
+    const bool aligned = (((uintptr_t)U | (uintptr_t)V) & 15) == 0 && (ld & 1) == 0;
+    if (use_tma && aligned && n >= 4 * EW_BLOCK) {
+        constexpr int STAGES = (W <= 5) ? 2 : 3;       // small windows fit two blocks per SM; large ones run one block
+        const size_t smem = (size_t)STAGES * 2 * (W + 1) * EW_BLOCK * sizeof(double);
+        auto kern = k_gram_tma<W, MODE, STAGES>;
+        const int per_sm = pk_blocks_per_sm((const void*)kern, EW_BLOCK, smem);
+        long long cap = (long long)ctx->sm_count * per_sm;
+        if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
+        long long want = n / EW_BLOCK;
+        int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+        kern<<<grid, EW_BLOCK, smem, ctx->stream>>>(n, ld, U, nu, V, nv, j0, ra);
+        PK_LAUNCH_CHECK();
+        return PK_OK;
+    }
+    int grid = ew_grid(ctx, k_gram<W, MODE>, n, 1);   // register-heavy (6W accumulators): occupancy decides the grid
     k_gram<W, MODE><<<grid, EW_BLOCK, 0, ctx->stream>>>(n, ld, U, nu, V, nv, j0, ra);
     PK_LAUNCH_CHECK();
     return PK_OK;
