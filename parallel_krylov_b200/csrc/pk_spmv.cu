@@ -12,6 +12,8 @@
 // and sums are separately rounded: the library is built with -fmad=false).  Tiles whose nonzeros exceed the staging buffer
 // (long rows) are processed warp-per-row with a shuffle reduction instead.
 // Dense kernel: warp per row, 128-bit loads, no tensor cores (GEMV is HBM-bound).
+#include <stdlib.h>
+
 #include "pk_device.cuh"
 #include "pk_launch.h"
 
@@ -41,6 +43,7 @@ struct SpmvArgs {
     long long nnz_total;
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
+    int evict_first;        // CSR arrays are streamed with an L2 evict-first hint (keeps the vectors in L2)
     int reduce;             // 1: run the grid reduction (3 sums)
 };
 
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     }
     __syncthreads();
 
+    const unsigned long long l2pol = l2_evict_first_policy();
     // thread 0: issue the bulk copies of my i-th tile into stage i % STAGES (endpoints nb/ne already loaded)
     auto issue = [&](long long i, int nb, int ne) {
         const int s = (int)(i % STAGES);
@@ -220,10 +224,18 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         meta[s].bulk = ok ? 1 : 0;
         if (ok) {
             mbar_expect_tx(&full[s], (unsigned)(cnt * 12 + rcnt * 4));
-            bulk_g2s(st_rp(s), a.rowptr + ra0, (unsigned)(rcnt * 4), &full[s]);
-            if (cnt > 0) {
-                bulk_g2s(st_col(s), a.col + q0, (unsigned)(cnt * 4), &full[s]);
-                bulk_g2s(st_val(s), a.val + q0, (unsigned)(cnt * 8), &full[s]);
+            if (a.evict_first) {
+                bulk_g2s_hint(st_rp(s), a.rowptr + ra0, (unsigned)(rcnt * 4), &full[s], l2pol);
+                if (cnt > 0) {
+                    bulk_g2s_hint(st_col(s), a.col + q0, (unsigned)(cnt * 4), &full[s], l2pol);
+                    bulk_g2s_hint(st_val(s), a.val + q0, (unsigned)(cnt * 8), &full[s], l2pol);
+                }
+            } else {
+                bulk_g2s(st_rp(s), a.rowptr + ra0, (unsigned)(rcnt * 4), &full[s]);
+                if (cnt > 0) {
+                    bulk_g2s(st_col(s), a.col + q0, (unsigned)(cnt * 4), &full[s]);
+                    bulk_g2s(st_val(s), a.val + q0, (unsigned)(cnt * 8), &full[s]);
+                }
             }
         } else {
             mbar_arrive(&full[s]);
@@ -750,6 +762,11 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.row_lo2 = a.row_hi2 = 0;
     a.hrecv = nullptr; a.hseq = nullptr; a.hticket = nullptr; a.n_own = m->n_rows; a.n_halo = m->n_halo; a.recv_mask = 0; a.n_ranks = ctx->n_ranks;
     a.cap = m->tile_cap;
+    {
+        static int ef = -1;
+        if (ef < 0) { const char* e = getenv("PK_L2_HINT"); ef = e ? atoi(e) : 1; }
+        a.evict_first = ef;
+    }
     a.reduce = dots.w ? 1 : 0;
     int grid = 0;
 
