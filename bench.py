@@ -362,7 +362,7 @@ def run_ours(args):
     _, per_it_bytes = algorithmic_bytes(solver, k or 0, n, nnz)
     spmv_avg_ms = prof_ms.value / max(prof_n.value, 1)
     spmv_gbs = b_spmv_loc / (spmv_avg_ms * 1e-3) / 1e9 if spmv_avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_spmv_stream (y = A p, fused p.Ap)", "achieved": spmv_gbs, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_spmv_tma (y = A x with fused dots; TMA bulk-copy pipeline)", "achieved": spmv_gbs, "peak": peak,
                 "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": load_traffic(args.workload),
                 "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_avg_ms,
                 "launches_timed": int(prof_n.value), "peak_source": peak_src,

@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     double acc[3] = {0.0, 0.0, 0.0};
     // tile index space: tiles of [row_lo,row_hi) followed by tiles of [row_lo2,row_hi2)
     const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
-    const long long tiles_b = (HALO && a.row_hi2 > a.row_lo2) ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
+    const long long tiles_b = a.row_hi2 > a.row_lo2 ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
     const long long n_tiles = tiles_a + tiles_b;
     auto tile_rows = [&](long long tile, long long& r0, long long& rend) {
-        if (!HALO || tile < tiles_a) { r0 = a.row_lo + tile * BLOCK; rend = a.row_hi; }
+        if (tile < tiles_a) { r0 = a.row_lo + tile * BLOCK; rend = a.row_hi; }
         else { r0 = a.row_lo2 + (tile - tiles_a) * BLOCK; rend = a.row_hi2; }
     };
     const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -816,29 +816,31 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         // which the last launch finishes (fixed slot order => deterministic).
         PK_CHECK(pk_comm_halo_start(ctx, m, x, x1));
         const long long lo = m->interior_lo, hi = m->interior_hi;
-        const long long rlo[3] = {lo, 0, hi}, rhi[3] = {hi, lo, m->n_rows};
-        const int cap_each = ctx->red.max_blocks / 3;
-        int grids[3] = {0, 0, 0}, last = -1, total = 0;
-        for (int i = 0; i < 3; ++i) {
-            if (rhi[i] <= rlo[i]) continue;
-            a.row_lo = rlo[i]; a.row_hi = rhi[i];
-            PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grids[i], cap_each, 1));
-            total += grids[i];
-            last = i;
+        const int cap_each = ctx->red.max_blocks / 2;
+        SpmvArgs ai = a, ab = a;
+        ai.row_lo = lo; ai.row_hi = hi;
+        if (m->use_tma) {                    // one launch covers the rows above and below the interior
+            ab.row_lo = 0; ab.row_hi = lo; ab.row_lo2 = hi; ab.row_hi2 = m->n_rows;
+        } else {                             // plain kernel: single range per launch -> treat [0,lo) then [hi,n) separately
+            ab.row_lo = 0; ab.row_hi = lo;
         }
-        int off = 0;
+        SpmvArgs ac = a;
+        ac.row_lo = hi; ac.row_hi = m->use_tma ? hi : m->n_rows;     // third launch only for the plain kernel
+        int g_int = 0, g_bnd = 0, g_c = 0;
+        PK_CHECK(launch_stream_any(ctx, m, two, ai, ra, &g_int, cap_each, 1));
+        PK_CHECK(launch_stream_any(ctx, m, two, ab, ra, &g_bnd, cap_each / 2, 1));
+        PK_CHECK(launch_stream_any(ctx, m, two, ac, ra, &g_c, cap_each / 2, 1));
+        const int total = g_int + g_bnd + g_c;
+        PkRedArgs r1 = ra, r2 = ra, r3 = ra;
+        r1.block_off = 0; r1.nb_total = total; r1.store_only = (g_bnd + g_c > 0) ? 1 : 0;
+        r2.block_off = g_int; r2.nb_total = total; r2.store_only = (g_c > 0) ? 1 : 0;
+        r3.block_off = g_int + g_bnd; r3.nb_total = total; r3.store_only = 0;
         bool waited = false;
-        for (int i = 0; i < 3; ++i) {
-            if (i >= 1 && !waited) { PK_CHECK(pk_comm_halo_wait(ctx)); waited = true; }
-            if (grids[i] == 0) continue;
-            a.row_lo = rlo[i]; a.row_hi = rhi[i];
-            PkRedArgs r2 = ra;
-            r2.block_off = off;
-            r2.nb_total = total;
-            r2.store_only = (i != last) ? 1 : 0;
-            PK_CHECK(launch_stream_any(ctx, m, two, a, r2, &grids[i], cap_each, 2));
-            off += grids[i];
-        }
+        if (g_int > 0) PK_CHECK(launch_stream_any(ctx, m, two, ai, r1, &g_int, cap_each, 2));
+        PK_CHECK(pk_comm_halo_wait(ctx));
+        waited = true;
+        if (g_bnd > 0) PK_CHECK(launch_stream_any(ctx, m, two, ab, r2, &g_bnd, cap_each / 2, 2));
+        if (g_c > 0) PK_CHECK(launch_stream_any(ctx, m, two, ac, r3, &g_c, cap_each / 2, 2));
         if (!waited) PK_CHECK(pk_comm_halo_wait(ctx));
     }
     if (dots.w) return pk_finish_reduce(ctx, 3, dots.epi, -1, 0);
