@@ -6,9 +6,9 @@
         bench.py --gpus N --steps K --warmup W
 
 Headline workload (all N, strong scaling): CG on the 3-D 7-point Poisson system 512^3 (n = 134 217 728,
-nnz = 937 951 232), fp64, x0 = 0, tol = 1e-8, one *step* = one call of the public solver with an iteration cap of
-300 (BASELINE.json: "CG iters/s & achieved HBM GB/s, 3D Poisson fp64 at 1/2/4/8 B200"; the north-star scaling target
-is quoted on 512^3).  Inputs are far larger than L2 (11.8 GB of CSR + 1 GiB vectors), so no L2 flush is needed.
+nnz = 937 951 232), fp64, x0 = 0, tol = 1e-8, one *step* = one full solve through the public entry point (iteration
+cap 2500; it converges earlier) (BASELINE.json: "CG iters/s & achieved HBM GB/s, 3D Poisson fp64 at 1/2/4/8 B200"; the
+north-star scaling target is quoted on 512^3).  Inputs are far larger than L2 (11.8 GB of CSR + 1 GiB vectors), so no L2 flush is needed.
 
 ONE JSON line on stdout (rank 0).  Everything else goes to stderr.
 """
@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 
 # name -> (solver, k, matrix kind, dims, iteration cap per step)
 WORKLOADS = {
-    "cg_p3d512": ("cg", None, "stencil", (512, 512, 512), 300),
+    "cg_p3d512": ("cg", None, "stencil", (512, 512, 512), 2500),   # full solve: converges in ~1.9k iterations
     "cg_p3d256": ("cg", None, "stencil", (256, 256, 256), 500),
     "cg_p3d128": ("cg", None, "stencil", (128, 128, 128), 500),
     "cg_p2d256": ("cg", None, "stencil", (256, 256, 1), 763),
@@ -277,7 +277,7 @@ def run_ours(args):
     # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if not use_graph:
-        _lib.check(ctx.lib.pk_prof_begin(ctx.handle, 4096))
+        _lib.check(ctx.lib.pk_prof_begin(ctx.handle, 16384))
     barrier()
     if sampler:
         sampler.start()
