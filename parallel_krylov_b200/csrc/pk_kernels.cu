@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_s(long long n, const double* _
 //      v3/cpu/mrr.py:45-48 ; kskipmrr.py:65-69 / :89-93 with (zeta, eta) = coef[2j], coef[2j+1]
 __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const double* __restrict__ ar,
                                                          double* __restrict__ y, double* __restrict__ z,
-                                                         double* __restrict__ r, double* __restrict__ x, int cj,
+                                                         const double* r, double* r_out, double* __restrict__ x, int cj,
                                                          PkRedArgs ra) {
     if (pk_done(ra.st)) return;
     const double zeta = (cj < 0) ? ra.st->zeta : ra.st->coef[2 * cj];
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const doub
         ri = ri - yi;
         y[i] = yi;
         z[i] = zi;
-        r[i] = ri;
+        r_out[i] = ri;
         x[i] = x[i] - zi;
         acc[0] += ri * ri;
     }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const doub
 
 // ---- k-skip CG step: x += a Ap0 ; Ar0 -= a Ap1 ; Ap0 = Ar0 + b Ap0 ; sums[0] = Ar0.Ar0  — kskipcg.py:53-55 -----
 __global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* __restrict__ x,
-                                                          double* __restrict__ ar0, double* __restrict__ ap0,
+                                                          double* __restrict__ ar0, const double* ap0, double* ap0_out,
                                                           const double* __restrict__ ap1, int cj, PkRedArgs ra) {
     if (pk_done(ra.st)) return;
     const double alpha = ra.st->coef[2 * cj];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* _
         x[i] = x[i] + alpha * p0;
         double ri = ar0[i] - alpha * ap1[i];
         ar0[i] = ri;
-        ap0[i] = ri + beta * p0;
+        ap0_out[i] = ri + beta * p0;
         acc[0] += ri * ri;
     }
     if (ra.epi != EPI_KS_STEP) pk_grid_reduce<1, EW_BLOCK>(acc, ra);
@@ -413,16 +413,16 @@ int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y,
     return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
 }
 
-int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
-                         int cj, int epi) {
-    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, x, cj, red_args_n(ctx, epi, 1));
+int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, const double* r,
+                         double* r_out, double* x, int cj, int epi) {
+    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, r_out, x, cj, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }
 
-int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
-                          int epi) {
-    k_kscg_update<<<ew_grid(ctx, k_kscg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap1, cj, red_args_n(ctx, epi, 1));
+int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, const double* ap0, double* ap0_out,
+                          const double* ap1, int cj, int epi) {
+    k_kscg_update<<<ew_grid(ctx, k_kscg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, ar0, ap0, ap0_out, ap1, cj, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }

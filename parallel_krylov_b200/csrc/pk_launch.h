@@ -17,10 +17,10 @@ int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r);
 int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
                         int epi);
 int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r);
-int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, double* r, double* x,
-                         int cj, int epi);
-int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, double* ap0, const double* ap1, int cj,
-                          int epi);
+int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, const double* r,
+                         double* r_out, double* x, int cj, int epi);
+int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, const double* ap0, double* ap0_out,
+                          const double* ap1, int cj, int epi);
 int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const double* U, int nu, const double* V, int nv,
                    int njj, int final_epi);
 
@@ -28,7 +28,14 @@ int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const doubl
 struct PkDots {
     const double* w = nullptr;   // sums: [0] = w.y, [1] = y.y, [2] = w.w   (nullptr: no reduction)
     int epi = EPI_NONE;
+    // k-skip step fused into the row epilogue (see SpmvArgs in pk_spmv.cu); only the TMA CSR kernel supports it
+    int fuse = 0, cj = 0;
+    double* f_a = nullptr;
+    double* f_b = nullptr;
+    double* f_x = nullptr;
+    double* f_out = nullptr;
 };
+bool pk_mat_can_fuse(const pk_mat* m);
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
 int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result);
 

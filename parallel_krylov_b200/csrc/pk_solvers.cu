@@ -224,6 +224,12 @@ extern "C" int pk_mat_kernel_info(pk_mat* m, int* kind, int* tile_rows, int* til
 
 extern "C" int64_t pk_mat_ld(pk_mat* m) { return m ? m->ld : 0; }
 
+bool pk_mat_can_fuse(const pk_mat* m) {
+    const char* e = getenv("PK_FUSE");            // PK_FUSE=0: keep update and SpMV as separate kernels (A/B, tests)
+    const int allow = e ? atoi(e) : 1;
+    return allow && m->kind != MAT_DENSE && m->use_tma;
+}
+
 extern "C" int pk_mat_set_halo(pk_mat* m, int n_peers_total, const int64_t* send_off, const int64_t* recv_off,
                                const int32_t* d_send_idx, const int32_t* h_send_idx, int64_t interior_lo,
                                int64_t interior_hi) {
@@ -304,9 +310,9 @@ extern "C" int64_t pk_work_doubles(int method, int64_t ld, int k) {
     switch (method) {
         case PK_CG: nvec = 3; break;                       // r, p, v
         case PK_MRR: nvec = 4; break;                      // r, Ar, y, z
-        case PK_KSKIPCG: nvec = (k + 1) + (k + 2); break;  // Ar[0..k], Ap[0..k+1]
-        case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 1; break;          // Ar[0..k+1], Ay[0..k], z
-        case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 2; break;  // + best_x
+        case PK_KSKIPCG: nvec = (k + 1) + (k + 2) + 1; break;  // Ar[0..k], Ap[0..k+1], spare Ap0 (fused steps)
+        case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 2; break;          // Ar[0..k+1], Ay[0..k], z, spare Ar0
+        case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;  // + best_x
         default: return -1;
     }
     return nvec * ld;
@@ -461,7 +467,7 @@ struct Solve {
         PK_CHECK(run_batches(1, 1, [&]() -> int {
             PK_CHECK(apply(r, ar, y, EPI_MRR_GAMMA));             // Ar ; nu = y.Ar ; mu = y.y ; gamma
             PK_CHECK(pk_launch_mrr_s(ctx, n, ar, y, r));          // s = Ar - gamma y ; zeta, eta
-            PK_CHECK(pk_launch_mrr_update(ctx, n, ar, y, z, r, x, -1, EPI_MRR_STEP));
+            PK_CHECK(pk_launch_mrr_update(ctx, n, ar, y, z, r, r, x, -1, EPI_MRR_STEP));
             return PK_OK;
         }));
         return PK_OK;
@@ -472,6 +478,8 @@ struct Solve {
         const int k = o.k;
         auto Ar = [&](int j) { return vec(j); };                  // rows 0..k
         auto Ap = [&](int j) { return vec(k + 1 + j); };          // rows 0..k+1
+        double* spare = vec(2 * k + 3);                           // second home of Ap[0] for the fused steps
+        const bool fuse = pk_mat_can_fuse(A);
         PK_CHECK(initial_residual(Ar(0), Ap(0), Ap(1), EPI_CG_INIT));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         PK_CHECK(apply(Ap(0), Ap(1)));                            // invariant: Ap[1] = A Ap[0] at trip start
@@ -479,11 +487,28 @@ struct Solve {
             // basis: one pass over A advances both chains: (Ar[j], Ap[j+1]) = A (Ar[j-1], Ap[j])
             for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j - 1), Ar(j), Ap(j), Ap(j + 1)));
             PK_CHECK(pk_launch_gram(ctx, 1, n, ld, Ar(0), k + 1, Ap(0), k + 2, k + 2, EPI_GRAM_CG));
-            for (int j = 0; j <= k; ++j) {
-                PK_CHECK(pk_launch_kscg_update(ctx, n, x, Ar(0), Ap(0), Ap(1), j, j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
-                PK_CHECK(apply(Ap(0), Ap(1)));
+            if (!fuse) {
+                for (int j = 0; j <= k; ++j) {
+                    PK_CHECK(pk_launch_kscg_update(ctx, n, x, Ar(0), Ap(0), Ap(0), Ap(1), j,
+                                                   j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
+                    PK_CHECK(apply(Ap(0), Ap(1)));
+                }
+                return PK_OK;
             }
-            return PK_OK;
+            // All (alpha_j, beta_j) are known after the Gram kernel, so step j+1 rides in the epilogue of the SpMV that
+            // follows step j: Ap1 = A Ap0 is consumed in registers and never stored.  Ap0 ping-pongs between its home
+            // and `spare` (other rows still gather the old Ap0); step 0 picks the side so that it ends at home.
+            double* cur = (k % 2 == 1) ? spare : Ap(0);
+            PK_CHECK(pk_launch_kscg_update(ctx, n, x, Ar(0), Ap(0), cur, Ap(1), 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
+            for (int j = 1; j <= k; ++j) {
+                double* nxt = (cur == spare) ? Ap(0) : spare;
+                PkDots d;
+                d.epi = (j == k) ? EPI_KS_TRIP_END : EPI_KS_STEP;
+                d.fuse = 2; d.cj = j; d.f_a = Ar(0); d.f_x = x; d.f_out = nxt;
+                PK_CHECK(pk_launch_spmv(ctx, A, cur, nullptr, nullptr, nullptr, d));
+                cur = nxt;
+            }
+            return apply(Ap(0), Ap(1));                           // cur == Ap(0) here
         }));
         return PK_OK;
     }
@@ -498,13 +523,29 @@ struct Solve {
         auto Ar = [&](int j) { return vec(j); };                  // rows 0..k_alloc+1
         auto Ay = [&](int j) { return vec(k_alloc + 2 + j); };    // rows 0..k_alloc
         double* z = vec(2 * k_alloc + 3);
+        double* spare = vec(2 * k_alloc + 4);                     // second home of Ar[0] for the fused steps
         for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
         PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
-        for (int j = 0; j <= k; ++j) {
-            PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), x, j, j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
-            PK_CHECK(apply(Ar(0), Ar(1)));
+        if (!pk_mat_can_fuse(A)) {
+            for (int j = 0; j <= k; ++j) {
+                PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), Ar(0), x, j,
+                                              j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
+                PK_CHECK(apply(Ar(0), Ar(1)));
+            }
+            return PK_OK;
         }
-        return PK_OK;
+        // Fused steps (see kskipcg): Ar1 = A Ar0 lives only in registers; Ar0 ping-pongs between home and `spare`.
+        double* cur = (k % 2 == 1) ? spare : Ar(0);
+        PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), cur, x, 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
+        for (int j = 1; j <= k; ++j) {
+            double* nxt = (cur == spare) ? Ar(0) : spare;
+            PkDots d;
+            d.epi = (j == k) ? EPI_KS_TRIP_END : EPI_KS_STEP;
+            d.fuse = 1; d.cj = j; d.f_a = Ay(0); d.f_b = z; d.f_x = x; d.f_out = nxt;
+            PK_CHECK(pk_launch_spmv(ctx, A, cur, nullptr, nullptr, nullptr, d));
+            cur = nxt;
+        }
+        return apply(Ar(0), Ar(1));                               // cur == Ar(0) here
     }
     int kskipmrr() {
         const int k = o.k;
@@ -522,7 +563,7 @@ struct Solve {
     int adaptive(int* final_k, int* host_converged) {
         const int k0 = o.k;
         int k = k0;
-        double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k0 + 2), *z = vec(2 * k0 + 3), *best_x = vec(2 * k0 + 4);
+        double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k0 + 2), *z = vec(2 * k0 + 3), *best_x = vec(2 * k0 + 5);
         PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         PK_CHECK(fetch_state());

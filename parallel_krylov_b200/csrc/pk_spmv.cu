@@ -44,6 +44,14 @@ struct SpmvArgs {
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
     int evict_first;        // CSR arrays are streamed with an L2 evict-first hint (keeps the vectors in L2)
+    // k-skip step fused into the row epilogue (coefficients of step cj are already in PkState::coef):
+    //   fuse 1 (MrR, x0 = Ar0): Ay0 = eta Ay0 + zeta y ; z = eta z - zeta Ar0 ; Ar0' = Ar0 - Ay0 ; x -= z   (y = A Ar0 not stored)
+    //   fuse 2 (CG,  x0 = Ap0): x += alpha Ap0 ; Ar0 -= alpha y ; Ap0' = Ar0 + beta Ap0                    (y = A Ap0 not stored)
+    int fuse, cj;
+    double* f_a;            // MrR: Ay0      | CG: Ar0 (in place)
+    double* f_b;            // MrR: z        | CG: unused
+    double* f_x;            // solution x
+    double* f_out;          // MrR: Ar0'     | CG: Ap0'   (a buffer different from x0: other rows still gather x0)
     int reduce;             // 1: run the grid reduction (3 sums)
 };
 
@@ -176,7 +184,7 @@ struct TileMeta {
     int pad;
 };
 
-template <int NV, int BLOCK, int STAGES, bool HALO>
+template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
 __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     if (pk_done(ra.st)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -190,6 +198,8 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc[3] = {0.0, 0.0, 0.0};
+    const double c0 = FUSE ? ra.st->coef[2 * a.cj] : 0.0;       // zeta | alpha
+    const double c1 = FUSE ? ra.st->coef[2 * a.cj + 1] : 0.0;   // eta  | beta
     // tile index space: tiles of [row_lo,row_hi) followed by tiles of [row_lo2,row_hi2)
     const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
     const long long tiles_b = a.row_hi2 > a.row_lo2 ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
@@ -283,6 +293,34 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     }
     const int n_own = (int)a.n_own;
 
+    // what a thread does with its finished row: store y (+ dots), or the fused k-skip step
+    auto finish_row = [&](long long row, double sum0, double sum1, double wi, double fa, double fb, double fx, double xr) {
+        if (FUSE == 0) {
+            a.y0[row] = sum0;
+            if (NV == 2) a.y1[row] = sum1;
+            if (a.w) {
+                acc[0] += wi * sum0;
+                acc[1] += sum0 * sum0;
+                acc[2] += wi * wi;
+            }
+        } else if (FUSE == 1) {           // kskipmrr.py:65-69 / :89-93 with (zeta, eta) = (c0, c1), Ar1 = sum0
+            const double ay = c1 * fa + c0 * sum0;
+            const double zz = c1 * fb - c0 * xr;
+            const double rn = xr - ay;
+            a.f_a[row] = ay;
+            a.f_b[row] = zz;
+            a.f_out[row] = rn;
+            a.f_x[row] = fx - zz;
+            acc[0] += rn * rn;
+        } else {                          // kskipcg.py:53-55 / :69-71 with (alpha, beta) = (c0, c1), Ap1 = sum0
+            a.f_x[row] = fx + c0 * xr;
+            const double rn = fa - c0 * sum0;
+            a.f_a[row] = rn;
+            a.f_out[row] = rn + c1 * xr;
+            acc[0] += rn * rn;
+        }
+    };
+
     for (long long i = 0; i < my_tiles; ++i) {
         const int s = (int)(i % STAGES);
         if (tid == 0) {
@@ -323,7 +361,12 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
             if (tid < nr) {
                 const int sb = rp[rofs + tid] - q0, se = rp[rofs + tid + 1] - q0;
                 const long long row = r0 + tid;
-                const double wi = a.w ? __ldg(a.w + row) : 0.0;      // issued before the row loop: latency hidden
+                // operands of the epilogue are requested before the row loop: their latency is hidden behind it
+                const double wi = (FUSE == 0 && a.w) ? __ldg(a.w + row) : 0.0;
+                const double fa = FUSE ? a.f_a[row] : 0.0;
+                const double fb = (FUSE == 1) ? a.f_b[row] : 0.0;
+                const double fx = FUSE ? a.f_x[row] : 0.0;
+                const double xr = FUSE ? __ldg(a.x0 + row) : 0.0;
                 double sum0 = 0.0, sum1 = 0.0;
                 constexpr int UNR = 8;
                 for (int j = sb; j < se; j += UNR) {
@@ -353,13 +396,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                         }
                     }
                 }
-                a.y0[row] = sum0;
-                if (NV == 2) a.y1[row] = sum1;
-                if (a.w) {
-                    acc[0] += wi * sum0;
-                    acc[1] += sum0 * sum0;
-                    acc[2] += wi * wi;
-                }
+                finish_row(row, sum0, sum1, wi, fa, fb, fx, xr);
             }
         } else {
             for (int r = warp; r < nr; r += NW) {
@@ -383,14 +420,8 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                 }
                 if (lane == 0) {
                     const long long row = r0 + r;
-                    a.y0[row] = sum0;
-                    if (NV == 2) a.y1[row] = sum1;
-                    if (a.w) {
-                        const double wi = a.w[row];
-                        acc[0] += wi * sum0;
-                        acc[1] += sum0 * sum0;
-                        acc[2] += wi * wi;
-                    }
+                    finish_row(row, sum0, sum1, (FUSE == 0 && a.w) ? a.w[row] : 0.0, FUSE ? a.f_a[row] : 0.0,
+                               (FUSE == 1) ? a.f_b[row] : 0.0, FUSE ? a.f_x[row] : 0.0, FUSE ? a.x0[row] : 0.0);
                 }
             }
         }
@@ -587,7 +618,7 @@ int launch_plain_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedA
 }
 
 // ---- TMA variant launcher ------------------------------------------------------------------------------------------
-template <int NV, int BLOCK, int STAGES, bool HALO>
+template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
 int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int grid_cap, int mode) {
     const size_t stage_bytes = (((size_t)a.cap * 12 + (BLOCK + 8) * 4) + 127) / 128 * 128;
     const size_t smem = stage_bytes * STAGES;
@@ -597,7 +628,7 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
     const long long n_tiles = (n_rows > 0 ? (n_rows + BLOCK - 1) / BLOCK : 0) + (n_rows2 + BLOCK - 1) / BLOCK;
     int grid = *grid_io;
     if (mode != 2) {
-        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO>, BLOCK, smem);
+        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO, FUSE>, BLOCK, smem);
         long long g = (long long)ctx->sm_count * per_sm;
         if (g > n_tiles) g = n_tiles;
         if (g > grid_cap) g = grid_cap;
@@ -605,9 +636,9 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
         *grid_io = grid;
         if (mode == 1) return PK_OK;
     } else {
-        pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO>, BLOCK, smem);   // sets the smem attribute
+        pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO, FUSE>, BLOCK, smem);   // sets the smem attribute
     }
-    k_spmv_tma<NV, BLOCK, STAGES, HALO><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
+    k_spmv_tma<NV, BLOCK, STAGES, HALO, FUSE><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         pk_set_error("spmv(tma) launch (grid %d, smem %zu): %s", grid, smem, cudaGetErrorString(e));
@@ -619,11 +650,19 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
 
 template <int NV, int BLOCK>
 int launch_tma_stages(pk_ctx* ctx, int stages, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
-    if (a.hrecv != nullptr) return launch_tma<NV, BLOCK, 2, true>(ctx, a, ra, grid_io, cap, mode);
+    if (NV == 1 && a.fuse == 1) {
+        if (a.hrecv != nullptr) return launch_tma<1, BLOCK, 2, true, 1>(ctx, a, ra, grid_io, cap, mode);
+        return launch_tma<1, BLOCK, 2, false, 1>(ctx, a, ra, grid_io, cap, mode);
+    }
+    if (NV == 1 && a.fuse == 2) {
+        if (a.hrecv != nullptr) return launch_tma<1, BLOCK, 2, true, 2>(ctx, a, ra, grid_io, cap, mode);
+        return launch_tma<1, BLOCK, 2, false, 2>(ctx, a, ra, grid_io, cap, mode);
+    }
+    if (a.hrecv != nullptr) return launch_tma<NV, BLOCK, 2, true, 0>(ctx, a, ra, grid_io, cap, mode);
     switch (stages) {
-        case 3: return launch_tma<NV, BLOCK, 3, false>(ctx, a, ra, grid_io, cap, mode);
-        case 4: return launch_tma<NV, BLOCK, 4, false>(ctx, a, ra, grid_io, cap, mode);
-        default: return launch_tma<NV, BLOCK, 2, false>(ctx, a, ra, grid_io, cap, mode);
+        case 3: return launch_tma<NV, BLOCK, 3, false, 0>(ctx, a, ra, grid_io, cap, mode);
+        case 4: return launch_tma<NV, BLOCK, 4, false, 0>(ctx, a, ra, grid_io, cap, mode);
+        default: return launch_tma<NV, BLOCK, 2, false, 0>(ctx, a, ra, grid_io, cap, mode);
     }
 }
 
@@ -731,7 +770,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.epi = dots.epi;
     ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p) ? 1 : 0;
     ra.p2p = ctx->d_p2p;
-    ra.ar_n = dots.w ? 3 : 0;
+    ra.ar_n = dots.w ? 3 : ((dots.fuse && dots.epi != EPI_KS_STEP) ? 1 : 0);
     ra.g_off = -1;
     ra.block_off = 0;
     ra.nb_total = 0;
@@ -757,6 +796,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
     a.x0 = x; a.x1 = x1; a.y0 = y; a.y1 = y1; a.w = dots.w;
     a.w_is_x = (dots.w == x) ? 1 : 0;
+    a.fuse = dots.fuse; a.cj = dots.cj; a.f_a = dots.f_a; a.f_b = dots.f_b; a.f_x = dots.f_x; a.f_out = dots.f_out;
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
     a.row_lo2 = a.row_hi2 = 0;
@@ -767,7 +807,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         if (ef < 0) { const char* e = getenv("PK_L2_HINT"); ef = e ? atoi(e) : 1; }
         a.evict_first = ef;
     }
-    a.reduce = dots.w ? 1 : 0;
+    a.reduce = (dots.w || (dots.fuse && dots.epi != EPI_KS_STEP)) ? 1 : 0;
     int grid = 0;
 
     if (!m->distributed || m->n_halo == 0) {
@@ -844,5 +884,6 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         if (!waited) PK_CHECK(pk_comm_halo_wait(ctx));
     }
     if (dots.w) return pk_finish_reduce(ctx, 3, dots.epi, -1, 0);
+    if (dots.fuse && dots.epi != EPI_KS_STEP) return pk_finish_reduce(ctx, 1, dots.epi, -1, 0);
     return PK_OK;
 }

@@ -27,7 +27,7 @@ def test_header_symbols_exported_and_bound():
     assert set(_lib.exported_symbols()) == set(names), set(_lib.exported_symbols()) ^ set(names)
     assert lib.pk_version() == 100
     assert lib.pk_work_doubles(0, 1024, 0) == 3 * 1024          # cg: r, p, v
-    assert lib.pk_work_doubles(3, 1024, 8) == (10 + 9 + 1) * 1024
+    assert lib.pk_work_doubles(3, 1024, 8) == (10 + 9 + 2) * 1024   # Ar, Ay, z, spare Ar0
 
 
 def test_struct_layouts_match_header():

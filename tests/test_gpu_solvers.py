@@ -90,6 +90,18 @@ def test_graph_and_stream_paths_agree_bitwise(pk, solver, k):
         assert np.array_equal(i1["nosl"], ii["nosl"])
 
 
+@pytest.mark.parametrize("solver,k", [("kskipcg", 1), ("kskipcg", 4), ("kskipmrr", 3), ("kskipmrr", 8), ("adaptivekskipmrr", 4)])
+def test_fused_steps_are_bitwise_identical_to_separate_kernels(pk, solver, k, monkeypatch):
+    """The k-skip step fused into the SpMV epilogue performs the same roundings as update kernel + SpMV."""
+    case = {"matrix": "p3d12x20x9", "rhs": "randn", "solver": solver, "k": k, "tol": 1e-8, "maxiter": None}
+    monkeypatch.setenv("PK_FUSE", "1")
+    _, _, x1, i1 = _run(pk, case)
+    monkeypatch.setenv("PK_FUSE", "0")
+    _, _, x0, i0 = _run(pk, case)
+    assert np.array_equal(x1, x0) and np.array_equal(i1["residual"], i0["residual"])
+    assert i1["gpu_launches"] < i0["gpu_launches"]
+
+
 def test_initial_guess_and_device_inputs(pk):
     """x given as ndarray is an initial guess (v3/gpu/common.py:30-33); torch CUDA inputs are used in place."""
     case = {"matrix": "p2d48", "rhs": "randn", "solver": "cg", "k": None, "tol": 1e-8, "maxiter": None}
