@@ -9,7 +9,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <map>
 
 #include "pk_common.cuh"
 #include "pk_launch.h"
@@ -75,6 +74,7 @@ extern "C" int pk_ctx_destroy(pk_ctx* c) {
     cudaFree(c->red.partials);
     cudaFree(c->red.ticket);
     cudaFree(c->d_state);
+    if (c->my_mbox) cudaFree(c->my_mbox);
     cudaFreeHost(c->h_state);
     cudaFreeHost(c->h_flags);
     cudaStreamDestroy(c->side);
@@ -239,7 +239,10 @@ extern "C" int pk_mat_set_halo(pk_mat* m, int n_peers_total, const int64_t* send
     m->send_off.assign(send_off, send_off + P + 1);
     m->recv_off.assign(recv_off, recv_off + P + 1);
     m->n_halo = recv_off[P];
-    PK_REQUIRE(m->n_rows + m->n_halo <= m->n_cols || m->kind == MAT_DENSE || true, "halo larger than column space");
+    PK_REQUIRE(m->kind == MAT_DENSE || m->n_rows + m->n_halo <= m->n_cols, "halo larger than the column space of the block");
+    for (int p = 0; p < P; ++p)
+        PK_REQUIRE(send_off[p + 1] >= send_off[p] && recv_off[p + 1] >= recv_off[p], "offsets must be non-decreasing");
+    PK_REQUIRE(send_off[P] == 0 || (d_send_idx != nullptr && h_send_idx != nullptr), "null send index list");
     m->d_send_idx = d_send_idx;
     m->send_contig.assign(P, 0);
     m->send_first.assign(P, 0);
@@ -646,6 +649,11 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     float ms = 0.f;
     PK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
     const PkState* h = ctx->h_state;
+    if (h->guard < 0) {
+        pk_set_error("a peer rank never delivered its %s (in-kernel wait timed out); solve aborted",
+                     h->guard == -1 ? "all-reduce contribution" : "halo");
+        return PK_ERR_NCCL;
+    }
     result->iterations = h->it;
     result->entries = h->idx + 1;
     result->converged = host_conv >= 0 ? host_conv : h->converged;

@@ -13,6 +13,31 @@ which = sys.argv[1] if len(sys.argv) > 1 else "p3d256"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 ctx = Context.get(0)
 lib = ctx.lib
+if which.startswith("dense"):
+    nd = int(which[5:] or 16384)
+    a = torch.empty(nd, nd, dtype=torch.float64, device="cuda").normal_()
+    op = Operator.from_dense_tensor(a, ctx)
+    ld = op.ld
+    xs = [dp.hash_normal(i, ld) for i in range(2)]
+    y0 = torch.empty(ld, dtype=torch.float64, device="cuda"); y1 = torch.empty_like(y0)
+    sums = torch.zeros(3, dtype=torch.float64, device="cuda")
+    N0 = C.c_void_p(0)
+    def timeit(fn, nbytes, label):
+        for _ in range(3): fn()
+        ctx.sync(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record(); torch.cuda.synchronize(); ctx.sync()
+        ms = e0.elapsed_time(e1) / reps
+        print(f"{label:34s} {ms*1e3:9.1f} us  {nbytes/ms/1e6:8.1f} GB/s  {100*nbytes/ms/1e6/6556.5:5.1f}% of measured peak")
+    bts = 8.0 * nd * nd + 16.0 * nd
+    timeit(lambda: _lib.check(lib.pk_spmv(ctx.handle, op.handle, _ptr(xs[0]), _ptr(y0), N0, N0, N0, N0)), bts, f"gemv {nd}x{nd}")
+    timeit(lambda: _lib.check(lib.pk_spmv(ctx.handle, op.handle, _ptr(xs[0]), _ptr(y0), N0, N0, _ptr(xs[0]), _ptr(sums))), bts, "gemv + fused dots")
+    timeit(lambda: _lib.check(lib.pk_spmv(ctx.handle, op.handle, _ptr(xs[0]), _ptr(y0), _ptr(xs[1]), _ptr(y1), N0, N0)), bts, "gemv two chains (one pass over A)")
+    ref = a @ xs[0][:nd]
+    print("max rel err vs torch:", float((y0[:nd] - (a @ xs[0][:nd])).abs().max() / ref.abs().max()))
+    sys.exit(0)
 if which.startswith("p3d"):
     d = int(which[3:]); rowptr, col, val, n = dp.stencil_csr(d, d, d)
 elif which.startswith("p2d"):
