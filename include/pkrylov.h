@@ -73,6 +73,16 @@ int pk_mat_destroy(pk_mat* mat);
  * 1 = csr-vector (warp per row), 2 = dense gemv.  *tile_rows / *tile_cap describe the stream tiling. */
 int pk_mat_kernel_info(pk_mat* mat, int* kind, int* tile_rows, int* tile_cap);
 
+/* Row-pattern compression (opt-in, lossless).  Rows with the same (column offset from the row, value) sequence share
+ * one table entry; the block is then applied from one 16-bit id per row (constant-coefficient stencils: 2 bytes per row
+ * instead of 12 per nonzero) with the same products in the same order as the CSR kernels.  pk_mat_row_hashes gives a
+ * 64-bit hash per row to group rows by; pk_mat_set_patterns verifies on the device that EVERY row reproduces its pattern
+ * bit for bit (else PK_ERR_ARG and the CSR kernels stay in use).  Table limits: <= 65535 patterns, 12*entries +
+ * 4*(patterns+1) <= 64 KiB.  All arrays are borrowed device pointers. */
+int pk_mat_row_hashes(pk_mat* mat, uint64_t* d_hash);
+int pk_mat_set_patterns(pk_mat* mat, int n_pat, int n_entries, const uint16_t* d_id, const int32_t* d_ptr,
+                        const int32_t* d_off, const double* d_val);
+
 /* Halo plan for a distributed block (replaces the full-vector memcpyPeer broadcast v3/gpu/mpi/common.py:144 and
  * comm.Allgather :163).  For each peer p: this rank sends send_count[p] owned entries, listed (local indices) in
  * d_send_idx[send_off[p] .. send_off[p+1]), and receives recv_count[p] entries into the halo tail at

@@ -145,6 +145,8 @@ class Operator:
         self.h2d_bytes = 0
         self.n_halo = 0
         self.row_offsets = None
+        self.compressed = False
+        self.n_patterns = 0
 
     def __del__(self):
         try:
@@ -161,8 +163,8 @@ class Operator:
     def kernel_info(self):
         k, r, c = C.c_int(), C.c_int(), C.c_int()
         check(self.ctx.lib.pk_mat_kernel_info(self.handle, C.byref(k), C.byref(r), C.byref(c)))
-        return {"kernel": ["csr-stream", "csr-vector", "dense-gemv"][k.value], "tile_rows": r.value,
-                "tile_cap": c.value}
+        return {"kernel": "row-pattern" if self.compressed else ["csr-stream", "csr-vector", "dense-gemv"][k.value],
+                "tile_rows": r.value, "tile_cap": c.value, "patterns": self.n_patterns}
 
     # -- constructors -------------------------------------------------------------------------------------------
     @classmethod
@@ -233,6 +235,52 @@ class Operator:
                                         m.shape[1], ctx)
         raise PkError(f"unsupported matrix type {type(A)!r}")
 
+    # -- opt-in lossless compression ------------------------------------------------------------------------------
+    def compress_patterns(self) -> bool:
+        """Group rows by their (column offset from the row, value) sequence and, if the table of distinct patterns is
+        small (≤ 32767 patterns, ≤ 64 KiB), switch the operator to the pattern kernel: one 16-bit id per row instead of
+        12 bytes per nonzero, same products in the same order (bit-identical results).  Returns whether it applied.
+        Constant-coefficient stencils compress (27 patterns for the 3-D 7-point Laplacian); matrices with distinct
+        values per row (e.g. ``problems.banded_spd``) do not and keep the CSR kernels.  The device verifies every row
+        against its pattern before the switch."""
+        if self.kind != "csr" or self.n_rows == 0 or self.compressed:
+            return self.compressed
+        ctx, dev, n = self.ctx, self.ctx.torch_device, self.n_rows
+        rowptr, col, val = self.tensors["rowptr"], self.tensors["col"], self.tensors["val"]
+        hashes = torch.empty(n, dtype=torch.int64, device=dev)
+        torch.cuda.current_stream(ctx.device).synchronize()
+        with torch.cuda.device(ctx.device):
+            check(ctx.lib.pk_mat_row_hashes(self.handle, _ptr(hashes)), "pk_mat_row_hashes")
+            ctx.sync()
+            uniq, inv = torch.unique(hashes, return_inverse=True)
+            del hashes
+            n_pat = int(uniq.numel())
+            if n_pat > 32767:
+                return False
+            rep = torch.full((n_pat,), n, dtype=torch.int64, device=dev)
+            rep.scatter_reduce_(0, inv, torch.arange(n, device=dev), reduce="amin")      # first row of each pattern
+            rp64 = rowptr.to(torch.int64)
+            lens = rp64[rep + 1] - rp64[rep]
+            n_ent = int(lens.sum().item())
+            if 12 * n_ent + 4 * (n_pat + 1) > 64 * 1024:
+                return False
+            ptr = torch.zeros(n_pat + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens, 0, out=ptr[1:])
+            seg = torch.repeat_interleave(torch.arange(n_pat, device=dev), lens)
+            src = rp64[rep[seg]] + (torch.arange(n_ent, device=dev) - ptr[seg])
+            off = (col[src].to(torch.int64) - rep[seg]).to(torch.int32).contiguous()
+            pval = val[src].contiguous()
+            ids = inv.to(torch.int16).contiguous()               # < 32768 patterns: the bits are the uint16 id
+            del inv
+            ptr32 = ptr.to(torch.int32).contiguous()
+            rc = ctx.lib.pk_mat_set_patterns(self.handle, n_pat, n_ent, _ptr(ids), _ptr(ptr32), _ptr(off), _ptr(pval))
+        if rc != 0:
+            return False
+        self.tensors.update({"pat_id": ids, "pat_ptr": ptr32, "pat_off": off, "pat_val": pval})
+        self.compressed = True
+        self.n_patterns = n_pat
+        return True
+
     # -- building blocks (tests / benchmarks) ------------------------------------------------------------------
     def matvec(self, x: torch.Tensor, dot_with: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None):
         """y = A x through the solver's operator kernel.  Returns y (and y1), plus the fused sums when asked."""
@@ -290,7 +338,8 @@ def quiet() -> bool:
 
 
 def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_every: int = 0,
-          use_graph: Optional[bool] = None, verbose: Optional[bool] = None, ctx: Optional[Context] = None):
+          use_graph: Optional[bool] = None, verbose: Optional[bool] = None, ctx: Optional[Context] = None,
+          compress: Optional[bool] = None):
     """Shared body of the five entry points.  Returns ``(x, info)`` like the reference
     (/root/reference/v3/gpu/cg.py:47-52): x and the histories are torch CUDA tensors."""
     op = Operator.from_any(A, ctx)
@@ -298,6 +347,10 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
     dev = ctx.torch_device
     lib = ctx.lib
     n = op.n_rows
+    if compress is None:
+        compress = os.environ.get("PK_COMPRESS", "0") not in ("0", "")
+    if compress:
+        op.compress_patterns()           # opt-in, lossless; silently keeps CSR when the matrix has no repeating rows
     if op.n_global != n and op.row_offsets is None:
         raise PkError(f"A must be square (got {n} x {op.n_global}); use parallel_krylov_b200.mpi for row blocks")
     ld = op.ld

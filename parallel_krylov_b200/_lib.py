@@ -46,6 +46,8 @@ _SIGS = {
     "pk_mat_destroy": (C.c_int, [_P]),
     "pk_mat_kernel_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pk_mat_ld": (_I64, [_P]),
+    "pk_mat_row_hashes": (C.c_int, [_P, _P]),
+    "pk_mat_set_patterns": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pk_mat_set_halo": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _I64, _I64]),
     "pk_mat_halo_p2p_handle": (C.c_int, [_P, C.c_char_p]),
     "pk_mat_halo_p2p_open": (C.c_int, [_P, C.c_char_p, _P, _P]),

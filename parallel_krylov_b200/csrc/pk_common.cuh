@@ -188,5 +188,14 @@ struct pk_mat {
     std::vector<void*> peer_recv_maps;           // IPC mappings to close
     long long interior_lo = 0, interior_hi = 0;
     long long ld = 0;
+    // Row-pattern compression (opt-in, lossless): rows that share the same (column offsets relative to the row, values)
+    // sequence are stored once in a small table; the matrix becomes one 16-bit pattern id per row.  Constant-coefficient
+    // stencils have a few dozen patterns (27 for the 3-D 7-point Laplacian), so A shrinks from ~84 to 2 bytes per row.
+    bool pat_on = false;
+    int n_pat = 0, pat_entries = 0;
+    const uint16_t* pat_id = nullptr;      // [n_rows]
+    const int32_t* pat_ptr = nullptr;      // [n_pat + 1]
+    const int32_t* pat_off = nullptr;      // [pat_entries]  col - row
+    const double* pat_val = nullptr;       // [pat_entries]
 };
 

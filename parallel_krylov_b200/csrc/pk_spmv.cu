@@ -441,6 +441,148 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
 }
 
+// --------------------------------------------------------------------------------------------------------------
+// Pattern-compressed operator (opt-in): one 16-bit id per row selects a (offsets, values) sequence from a table held in
+// shared memory.  Thread per row, left-to-right accumulation with the table's values — the same products and the same
+// order as the CSR kernels, hence the same bits — but the matrix costs 2 bytes per row instead of 12 per nonzero.
+// Neighbouring rows almost always share a pattern, so a warp's gathers are fully coalesced.
+struct PatArgs {
+    const uint16_t* id;
+    const int32_t* ptr;
+    const int32_t* off;
+    const double* val;
+    int n_pat, n_ent;
+};
+
+template <int NV, int FUSE>
+__global__ void __launch_bounds__(256) k_spmv_pat(PatArgs pa, SpmvArgs a, PkRedArgs ra) {
+    if (pk_done(ra.st)) return;
+    extern __shared__ __align__(16) unsigned char psm[];
+    double* tval = reinterpret_cast<double*>(psm);                 // [n_ent]
+    int* toff = reinterpret_cast<int*>(tval + pa.n_ent);           // [n_ent]
+    int* tptr = toff + pa.n_ent;                                   // [n_pat + 1]
+    for (int t = threadIdx.x; t < pa.n_ent; t += 256) { tval[t] = pa.val[t]; toff[t] = pa.off[t]; }
+    for (int t = threadIdx.x; t <= pa.n_pat; t += 256) tptr[t] = pa.ptr[t];
+    __syncthreads();
+    double acc[3] = {0.0, 0.0, 0.0};
+    const double c0 = FUSE ? ra.st->coef[2 * a.cj] : 0.0;
+    const double c1 = FUSE ? ra.st->coef[2 * a.cj + 1] : 0.0;
+    const long long na = a.row_hi > a.row_lo ? a.row_hi - a.row_lo : 0;
+    const long long nb = a.row_hi2 > a.row_lo2 ? a.row_hi2 - a.row_lo2 : 0;
+    // R rows per thread are in flight together (ids, epilogue operands and gathers of all R rows are independent):
+    // this kernel moves ~20 bytes per row, so it needs thousands of rows in flight per SM to cover DRAM latency.
+    constexpr int R = (FUSE == 0 && NV == 1) ? 4 : 2;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long t0 = (long long)blockIdx.x * 256 + threadIdx.x; t0 < na + nb; t0 += R * stride) {
+        long long row[R];
+        int sb[R], len[R];
+        double wi[R], fa[R], fb[R], fx[R], xr[R], sum0[R], sum1[R];
+        int id[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long t = t0 + r * stride;
+            const bool ok = t < na + nb;
+            row[r] = ok ? (t < na ? a.row_lo + t : a.row_lo2 + (t - na)) : -1;
+            id[r] = ok ? (int)pa.id[row[r]] : 0;
+        }
+        int maxlen = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool ok = row[r] >= 0;
+            sb[r] = tptr[id[r]];
+            len[r] = ok ? tptr[id[r] + 1] - sb[r] : 0;
+            maxlen = len[r] > maxlen ? len[r] : maxlen;
+            wi[r] = (ok && FUSE == 0 && a.w) ? __ldg(a.w + row[r]) : 0.0;
+            fa[r] = (ok && FUSE) ? a.f_a[row[r]] : 0.0;
+            fb[r] = (ok && FUSE == 1) ? a.f_b[row[r]] : 0.0;
+            fx[r] = (ok && FUSE) ? a.f_x[row[r]] : 0.0;
+            xr[r] = (ok && FUSE) ? __ldg(a.x0 + row[r]) : 0.0;
+            sum0[r] = 0.0;
+            sum1[r] = 0.0;
+        }
+#pragma unroll 4
+        for (int j = 0; j < maxlen; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (j < len[r]) {                     // left-to-right within each row: the CSR / scipy order
+                    const long long c = row[r] + toff[sb[r] + j];
+                    const double v = tval[sb[r] + j];
+                    sum0[r] += v * __ldg(a.x0 + c);
+                    if (NV == 2) sum1[r] += v * __ldg(a.x1 + c);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (row[r] < 0) continue;
+            const long long rw = row[r];
+            if (FUSE == 0) {
+                a.y0[rw] = sum0[r];
+                if (NV == 2) a.y1[rw] = sum1[r];
+                if (a.w) {
+                    acc[0] += wi[r] * sum0[r];
+                    acc[1] += sum0[r] * sum0[r];
+                    acc[2] += wi[r] * wi[r];
+                }
+            } else if (FUSE == 1) {
+                const double ay = c1 * fa[r] + c0 * sum0[r];
+                const double zz = c1 * fb[r] - c0 * xr[r];
+                const double rn = xr[r] - ay;
+                a.f_a[rw] = ay;
+                a.f_b[rw] = zz;
+                a.f_out[rw] = rn;
+                a.f_x[rw] = fx[r] - zz;
+                acc[0] += rn * rn;
+            } else {
+                a.f_x[rw] = fx[r] + c0 * xr[r];
+                const double rn = fa[r] - c0 * sum0[r];
+                a.f_a[rw] = rn;
+                a.f_out[rw] = rn + c1 * xr[r];
+                acc[0] += rn * rn;
+            }
+        }
+    }
+    if (a.reduce) pk_grid_reduce<3, 256>(acc, ra);
+}
+
+// one 64-bit hash per row over its (col - row, value bits) sequence; equal rows <=> equal hashes up to collisions,
+// which k_pattern_verify rules out exactly
+__global__ void k_row_hash(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                           const double* __restrict__ val, long long n_rows, unsigned long long* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(rowptr[r + 1] - rowptr[r]);
+        for (int q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+            const unsigned long long o = (unsigned long long)(long long)(col[q] - (int)r);
+            const unsigned long long v = (unsigned long long)__double_as_longlong(val[q]);
+            h ^= o + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h *= 0xBF58476D1CE4E5B9ull;
+            h ^= v + 0x94D049BB133111EBull + (h << 6) + (h >> 2);
+            h *= 0x94D049BB133111EBull;
+            h ^= h >> 29;
+        }
+        out[r] = h;
+    }
+}
+
+// every row must reproduce its pattern exactly (offsets and value bits); mismatches are counted
+__global__ void k_pattern_verify(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                 const double* __restrict__ val, long long n_rows, PatArgs pa, int* __restrict__ bad) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        const int id = pa.id[r];
+        bool ok = id < pa.n_pat;
+        if (ok) {
+            const int sb = pa.ptr[id], se = pa.ptr[id + 1];
+            ok = (se - sb) == (rowptr[r + 1] - rowptr[r]);
+            for (int j = 0; ok && j < se - sb; ++j) {
+                const int q = rowptr[r] + j;
+                ok = (col[q] - (int)r) == pa.off[sb + j] &&
+                     __double_as_longlong(val[q]) == __double_as_longlong(pa.val[sb + j]);
+            }
+        }
+        if (!ok) atomicAdd(bad, 1);
+    }
+}
+
 // Owner-side halo push: store the entries each peer needs straight into that peer's receive buffer over NVLink, fence,
 // then (last block) raise the sequence flags.  Replaces pack kernel + ncclSend/ncclRecv + the side stream.
 __global__ void __launch_bounds__(256) k_halo_push(PkHaloPush hp, const double* __restrict__ x0,
@@ -675,8 +817,45 @@ int launch_tma_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArg
                : launch_tma_stages<1, 256>(ctx, m->stages, a, ra, grid_io, cap, mode);
 }
 
+template <int NV, int FUSE>
+int launch_pat(pk_ctx* ctx, pk_mat* m, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int grid_cap, int mode) {
+    PatArgs pa{m->pat_id, m->pat_ptr, m->pat_off, m->pat_val, m->n_pat, m->pat_entries};
+    const size_t smem = (size_t)m->pat_entries * 12 + (size_t)(m->n_pat + 1) * 4 + 16;
+    const long long n_rows = (a.row_hi > a.row_lo ? a.row_hi - a.row_lo : 0) + (a.row_hi2 > a.row_lo2 ? a.row_hi2 - a.row_lo2 : 0);
+    if (n_rows <= 0) { *grid_io = 0; return PK_OK; }
+    int grid = *grid_io;
+    if (mode != 2) {
+        const int per_sm = pk_blocks_per_sm((const void*)k_spmv_pat<NV, FUSE>, 256, smem);
+        long long g = (long long)ctx->sm_count * per_sm;
+        const long long want = (n_rows + 511) / 512;
+        if (g > want) g = want;
+        if (g > grid_cap) g = grid_cap;
+        grid = (int)(g < 1 ? 1 : g);
+        *grid_io = grid;
+        if (mode == 1) return PK_OK;
+    } else {
+        pk_blocks_per_sm((const void*)k_spmv_pat<NV, FUSE>, 256, smem);
+    }
+    k_spmv_pat<NV, FUSE><<<grid, 256, smem, ctx->stream>>>(pa, a, ra);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pk_set_error("spmv(pattern) launch (grid %d, smem %zu): %s", grid, smem, cudaGetErrorString(e));
+        return PK_ERR_CUDA;
+    }
+    ctx->launches++;
+    return PK_OK;
+}
+
+int launch_pat_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
+    if (two) return launch_pat<2, 0>(ctx, m, a, ra, grid_io, cap, mode);
+    if (a.fuse == 1) return launch_pat<1, 1>(ctx, m, a, ra, grid_io, cap, mode);
+    if (a.fuse == 2) return launch_pat<1, 2>(ctx, m, a, ra, grid_io, cap, mode);
+    return launch_pat<1, 0>(ctx, m, a, ra, grid_io, cap, mode);
+}
+
 int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap,
                       int mode) {
+    if (m->pat_on && a.hrecv == nullptr) return launch_pat_any(ctx, m, two, a, ra, grid_io, cap, mode);
     if (m->use_tma) return launch_tma_any(ctx, m, two, a, ra, grid_io, cap, mode);
     return launch_plain_any(ctx, m, two, a, ra, grid_io, cap, mode);
 }
@@ -735,6 +914,52 @@ int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int ti
 }
 
 static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots);
+
+// ---- row-pattern compression: C-ABI ---------------------------------------------------------------------------------
+extern "C" int pk_mat_row_hashes(pk_mat* m, uint64_t* d_hash) {
+    PK_REQUIRE(m && d_hash, "null argument");
+    PK_REQUIRE(m->kind != MAT_DENSE, "row patterns apply to CSR blocks");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    int grid = (int)((m->n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    if (grid < 1) grid = 1;
+    k_row_hash<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, (unsigned long long*)d_hash);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+extern "C" int pk_mat_set_patterns(pk_mat* m, int n_pat, int n_entries, const uint16_t* d_id, const int32_t* d_ptr,
+                                   const int32_t* d_off, const double* d_val) {
+    PK_REQUIRE(m && d_id && d_ptr && d_off && d_val, "null argument");
+    PK_REQUIRE(m->kind != MAT_DENSE, "row patterns apply to CSR blocks");
+    PK_REQUIRE(n_pat >= 1 && n_pat <= 65535 && n_entries >= 0 && (size_t)n_entries * 12 + (size_t)(n_pat + 1) * 4 <= 64 * 1024,
+               "pattern table too large for shared memory");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    // exact verification: every row must equal its pattern bit for bit, otherwise the CSR path stays in use
+    PatArgs pa{d_id, d_ptr, d_off, d_val, n_pat, n_entries};
+    int* d_bad = nullptr;
+    int h_bad = 0;
+    PK_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    PK_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    int grid = (int)((m->n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    if (grid < 1) grid = 1;
+    k_pattern_verify<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, pa, d_bad);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bad);
+    if (h_bad != 0) {
+        pk_set_error("pattern table does not reproduce %d rows; CSR path kept", h_bad);
+        return PK_ERR_ARG;
+    }
+    m->pat_id = d_id; m->pat_ptr = d_ptr; m->pat_off = d_off; m->pat_val = d_val;
+    m->n_pat = n_pat; m->pat_entries = n_entries;
+    m->pat_on = true;
+    return PK_OK;
+}
 
 static void seg_mark(pk_ctx* ctx, int tag) {
     if (!ctx->prof_detail || !ctx->prof_on || ctx->seg_ev.size() > 60000) return;
@@ -859,13 +1084,13 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         const int cap_each = ctx->red.max_blocks / 2;
         SpmvArgs ai = a, ab = a;
         ai.row_lo = lo; ai.row_hi = hi;
-        if (m->use_tma) {                    // one launch covers the rows above and below the interior
+        if (m->use_tma || m->pat_on) {       // one launch covers the rows above and below the interior
             ab.row_lo = 0; ab.row_hi = lo; ab.row_lo2 = hi; ab.row_hi2 = m->n_rows;
         } else {                             // plain kernel: single range per launch -> treat [0,lo) then [hi,n) separately
             ab.row_lo = 0; ab.row_hi = lo;
         }
         SpmvArgs ac = a;
-        ac.row_lo = hi; ac.row_hi = m->use_tma ? hi : m->n_rows;     // third launch only for the plain kernel
+        ac.row_lo = hi; ac.row_hi = (m->use_tma || m->pat_on) ? hi : m->n_rows;     // third launch only for the plain kernel
         int g_int = 0, g_bnd = 0, g_c = 0;
         PK_CHECK(launch_stream_any(ctx, m, two, ai, ra, &g_int, cap_each, 1));
         PK_CHECK(launch_stream_any(ctx, m, two, ab, ra, &g_bnd, cap_each / 2, 1));

@@ -155,3 +155,37 @@ def test_device_generators_match_host(pk):
     assert np.array_equal(ci.cpu().numpy(), sl.indices) and np.array_equal(va.cpu().numpy(), sl.data)
     z = dp.hash_normal(0, 4096).cpu().numpy()
     np.testing.assert_allclose(z, problems.hash_normal(0, 4096), rtol=1e-12, atol=1e-14)
+
+
+def test_row_pattern_compression_is_bit_exact(pk):
+    """Opt-in lossless compression: same bits as scipy / the CSR kernels; matrices without repeating rows keep CSR."""
+    rowptr, col, val, n = problems.poisson3d(20, 17, 23)
+    A = problems.to_scipy(rowptr, col, val, n)
+    rng = np.random.default_rng(8)
+    x, x1, w = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    op = pk.Operator.from_any(A)
+    assert op.compress_patterns() and op.kernel_info()["kernel"] == "row-pattern" and op.n_patterns == 27
+    y, sums = op.matvec(torch.from_numpy(x), dot_with=torch.from_numpy(w))
+    assert np.array_equal(y.cpu().numpy(), A.dot(x))
+    np.testing.assert_allclose(sums.cpu().numpy(), [np.dot(w, A.dot(x)), np.dot(A.dot(x), A.dot(x)), np.dot(w, w)], rtol=1e-13)
+    y0, y1 = op.matvec(torch.from_numpy(x), x1=torch.from_numpy(x1))
+    assert np.array_equal(y0.cpu().numpy(), A.dot(x)) and np.array_equal(y1.cpu().numpy(), A.dot(x1))
+    band = pk.Operator.from_any(problems.to_scipy(*problems.banded_spd(40000, 13, 0)))
+    assert band.compress_patterns() is False and band.kernel_info()["kernel"] == "csr-stream"
+
+
+@pytest.mark.parametrize("solver,k", [("cg", None), ("mrr", None), ("kskipcg", 3), ("kskipmrr", 4), ("adaptivekskipmrr", 2)])
+def test_solvers_on_compressed_operator_match_csr_bitwise(pk, solver, k):
+    rowptr, col, val, n = problems.poisson3d(18)
+    A = problems.to_scipy(rowptr, col, val, n)
+    b = problems.rhs(n, "randn", 0)
+    kw = {"k": k} if k is not None else {}
+    x0, i0 = getattr(pk, solver)(A, b, tol=1e-8, **kw)
+    x1, i1 = getattr(pk, solver)(A, b, tol=1e-8, compress=True, **kw)
+    # every SpMV is bit-identical; dots reduced in the SpMV epilogue (cg, mrr) are summed over a different grid, so
+    # those trajectories agree to rounding; k-skip steps take their scalars from the (unchanged) Gram kernel
+    assert torch.equal(i0["nosl"], i1["nosl"])
+    np.testing.assert_allclose(i1["residual"].cpu().numpy(), i0["residual"].cpu().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(x1.cpu().numpy(), x0.cpu().numpy(), rtol=1e-8, atol=1e-12)
+    if solver == "kskipcg":          # no dot product comes out of an SpMV epilogue in this solver: identical bits
+        assert torch.equal(x0, x1)
