@@ -304,6 +304,26 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     value = iters / (elapsed_ms * 1e-3)
 
+    # ---- exposed communication per iteration (N > 1): same kernels with halo exchange and all-reduces switched off ---
+    exposed = None
+    if world > 1:
+        _lib.check(ctx.lib.pk_ctx_set_nocomm(ctx.handle, 1))
+        cap_nc = min(cap, 200)
+        solve(solver, op, b, tol=0.0, maxiter=cap_nc, use_graph=False, ctx=ctx, **kw)
+        barrier()
+        e0.record()
+        _, inc = solve(solver, op, b, tol=0.0, maxiter=cap_nc, use_graph=False, ctx=ctx, **kw)
+        e1.record()
+        barrier()
+        _lib.check(ctx.lib.pk_ctx_set_nocomm(ctx.handle, 0))
+        t = torch.tensor([e0.elapsed_time(e1) / max(inc["iterations"], 1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        compute_only_ms = float(t.item())
+        iter_ms = elapsed_ms / max(iters, 1)
+        exposed = {"iteration_us": 1e3 * iter_ms, "compute_only_us": 1e3 * compute_only_ms,
+                   "exposed_comm_us_per_iteration": 1e3 * (iter_ms - compute_only_ms),
+                   "how": "same solve with halo exchange and all-reduces disabled (pk_ctx_set_nocomm), max over ranks"}
+
     # ---- timed region 2: end to end through the public entry point with HOST buffers ---------------------------
     # (A, b in pinned host memory -> H2D every step, solve, x -> D2H every step)
     del op
@@ -406,7 +426,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "spmv_launch_count": int(spmvs),
         "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_total),
                 "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "exposed_comm": exposed,
     }
     emit(line)
     if world > 1:

@@ -105,6 +105,9 @@ int pk_mat_halo_p2p_open(pk_mat* mat, const char* handles, const int64_t* dst_of
 int pk_nccl_unique_id(const char* nccl_path, char id[PK_NCCL_ID_BYTES]);
 int pk_comm_init(pk_ctx* ctx, const char* nccl_path, int n_ranks, int rank, const char id[PK_NCCL_ID_BYTES]);
 int pk_comm_destroy(pk_ctx* ctx);
+/* Measurement aid: with nocomm != 0 a solve launches the same kernels but skips halo exchange and all-reduces (its
+ * results are meaningless); bench.py times it to report the exposed communication per iteration. */
+int pk_ctx_set_nocomm(pk_ctx* ctx, int on);
 /* Optional: all-reduce the dot products INSIDE the reducing kernels over NVLink peer memory (one mailbox per rank,
  * exported with CUDA IPC) instead of ncclAllReduce + a scalar kernel.  pk_p2p_handle returns this rank's 64-byte IPC
  * handle; after all-gathering the handles, pk_p2p_open(handles = n_ranks x 64 bytes) maps the peers and switches the

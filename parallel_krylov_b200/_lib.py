@@ -54,6 +54,7 @@ _SIGS = {
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "pk_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "pk_comm_destroy": (C.c_int, [_P]),
+    "pk_ctx_set_nocomm": (C.c_int, [_P, C.c_int]),
     "pk_p2p_handle": (C.c_int, [_P, C.c_char_p]),
     "pk_p2p_open": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
     "pk_allreduce_sum": (C.c_int, [_P, _P, _I64]),

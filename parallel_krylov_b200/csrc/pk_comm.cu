@@ -236,6 +236,14 @@ void pk_mat_halo_p2p_close(pk_mat* m) {
     m->halo_p2p = false;
 }
 
+// Measurement aid for bench.py ("exposed communication per iteration"): with nocomm set, a solve launches the same
+// kernels but skips the halo exchange and the all-reduces, so its time is the compute-only time of this rank.
+extern "C" int pk_ctx_set_nocomm(pk_ctx* ctx, int on) {
+    PK_REQUIRE(ctx != nullptr, "null context");
+    ctx->nocomm = on != 0;
+    return PK_OK;
+}
+
 extern "C" int pk_comm_destroy(pk_ctx* ctx) {
     if (ctx && ctx->d_p2p) {
         cudaStreamSynchronize(ctx->stream);
@@ -255,7 +263,7 @@ extern "C" int pk_comm_destroy(pk_ctx* ctx) {
 }
 
 int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s) {
-    if (!ctx->comm || ctx->n_ranks <= 1) return PK_OK;
+    if (!ctx->comm || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
     PK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, ctx->comm->comm, s));
     return PK_OK;
 }
@@ -291,7 +299,7 @@ __global__ void k_pack(const int32_t* __restrict__ idx, long long n, const doubl
 
 // Start the halo exchange of x (and x1) on the side stream: the main stream may run interior rows meanwhile.
 int pk_comm_halo_start(pk_ctx* ctx, pk_mat* m, double* x, double* x1) {
-    if (!m->distributed || m->n_halo == 0 || ctx->n_ranks <= 1) return PK_OK;
+    if (!m->distributed || m->n_halo == 0 || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
     PK_REQUIRE(ctx->comm != nullptr, "distributed operator without a communicator");
     const int P = ctx->n_ranks;
     const long long n_send = m->send_off[P];
@@ -335,7 +343,7 @@ int pk_comm_halo_start(pk_ctx* ctx, pk_mat* m, double* x, double* x1) {
 }
 
 int pk_comm_halo_wait(pk_ctx* ctx) {
-    if (ctx->n_ranks <= 1) return PK_OK;
+    if (ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
     PK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
     return PK_OK;
 }

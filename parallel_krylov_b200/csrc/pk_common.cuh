@@ -124,6 +124,7 @@ struct pk_ctx {
     double* my_mbox = nullptr;
     std::vector<void*> peer_mbox;    // opened IPC mappings (to close)
     int n_ranks = 1, rank = 0;
+    bool nocomm = false;             // measurement aid: same kernels, no halo exchange / all-reduce (numerically meaningless)
     long long launches = 0;          // kernels launched (statistics)
     long long spmvs = 0;
     // optional per-launch timing of the operator kernel (bench.py's roofline): event pairs around each application

@@ -298,12 +298,12 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
     ra.max_blocks = ctx->red.max_blocks;
     ra.st = ctx->d_state;
     ra.epi = epi;
-    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p) ? 1 : 0;
+    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;
     ra.g_off = g_off;
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
-    ra.p2p = ctx->d_p2p;
+    ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
     ra.ar_n = 0;          // set by the launcher: number of sums this kernel all-reduces
     return ra;
 }
@@ -369,7 +369,7 @@ int pk_launch_set_k(pk_ctx* ctx, int k) {
 // After a reducing kernel: single GPU -> nothing to do (the last block already ran the epilogue);
 // multi GPU -> all-reduce the published sums over NVLink, then run the scalar engine.
 int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done) {
-    if (ctx->n_ranks <= 1 || ctx->d_p2p) return PK_OK;   // single GPU, or all-reduced inside the kernel
+    if (ctx->n_ranks <= 1 || ctx->d_p2p || ctx->nocomm) return PK_OK;   // single GPU, or all-reduced inside the kernel
     double* buf = (g_off >= 0) ? (ctx->d_state->gram + g_off) : ctx->d_state->red;
     PK_CHECK(pk_comm_allreduce(ctx, buf, nsums, ctx->stream));
     if (epi != EPI_NONE && epi != EPI_GRAM_PART && epi != EPI_KS_STEP) return pk_launch_scalar(ctx, epi, ignore_done);
@@ -497,7 +497,7 @@ int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const doubl
         else PK_CHECK((gram_dispatch<1>(ctx, w, n, ld, U, nu, V, nv, j0, epi, ar_n)));
         j0 += w;
     }
-    if (ctx->n_ranks > 1 && !ctx->d_p2p) {
+    if (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) {
         PK_CHECK(pk_comm_allreduce(ctx, ctx->d_state->gram, 6LL * njj, ctx->stream));
         if (final_epi != EPI_NONE) PK_CHECK(pk_launch_scalar(ctx, final_epi, 0));
     }

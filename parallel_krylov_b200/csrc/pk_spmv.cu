@@ -993,8 +993,8 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.max_blocks = ctx->red.max_blocks;
     ra.st = ctx->d_state;
     ra.epi = dots.epi;
-    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p) ? 1 : 0;
-    ra.p2p = ctx->d_p2p;
+    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;
+    ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
     ra.ar_n = dots.w ? 3 : ((dots.fuse && dots.epi != EPI_KS_STEP) ? 1 : 0);
     ra.g_off = -1;
     ra.block_off = 0;
@@ -1038,7 +1038,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     if (!m->distributed || m->n_halo == 0) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
-    } else if (m->halo_p2p && m->use_tma) {
+    } else if (m->halo_p2p && m->use_tma && !ctx->nocomm) {
         // NVLink push path, one stream: [push my boundary entries into the peers' receive buffers + flags] ->
         // [interior rows] -> [boundary rows: wait for the peers' flags, read halo columns from the receive buffer].
         seg_mark(ctx, 0);
