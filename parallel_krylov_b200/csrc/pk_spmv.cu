@@ -13,6 +13,7 @@
 // (long rows) are processed warp-per-row with a shuffle reduction instead.
 // Dense kernel: warp per row, 128-bit loads, no tensor cores (GEMV is HBM-bound).
 #include <stdlib.h>
+#include <string.h>
 
 #include "pk_device.cuh"
 #include "pk_launch.h"
@@ -44,6 +45,7 @@ struct SpmvArgs {
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
     int evict_first;        // CSR arrays are streamed with an L2 evict-first hint (keeps the vectors in L2)
+    int blocked;            // tile -> block assignment: 1 contiguous chunks per block, 0 grid-strided
     // k-skip step fused into the row epilogue (coefficients of step cj are already in PkState::coef):
     //   fuse 1 (MrR, x0 = Ar0): Ay0 = eta Ay0 + zeta y ; z = eta z - zeta Ar0 ; Ar0' = Ar0 - Ay0 ; x -= z   (y = A Ar0 not stored)
     //   fuse 2 (CG,  x0 = Ap0): x += alpha Ap0 ; Ar0 -= alpha y ; Ap0' = Ar0 + beta Ap0                    (y = A Ap0 not stored)
@@ -208,7 +210,16 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         if (tile < tiles_a) { r0 = a.row_lo + tile * BLOCK; rend = a.row_hi; }
         else { r0 = a.row_lo2 + (tile - tiles_a) * BLOCK; rend = a.row_hi2; }
     };
-    const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Tile -> block assignment.  strided (default): tile = b + i*grid, i.e. the grid is one moving window over A.
+    // blocked (PK_TILE_ORDER=blocked): block b owns the contiguous tiles [b*chunk, (b+1)*chunk), which turns the
+    // +-(one grid line) gathers into L1 hits but splits HBM traffic into hundreds of streams — measured on B200 at
+    // 256^3: 301 us vs 254 us strided, so it stays an experiment switch.
+    const long long chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long first_tile = a.blocked ? (long long)blockIdx.x * chunk : (long long)blockIdx.x;
+    const long long tile_step = a.blocked ? 1 : (long long)gridDim.x;
+    const long long my_tiles = a.blocked
+        ? (first_tile < n_tiles ? (first_tile + chunk <= n_tiles ? chunk : n_tiles - first_tile) : 0)
+        : (n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     // thread 0: issue the bulk copies of my i-th tile into stage i % STAGES (endpoints nb/ne already loaded)
     auto issue = [&](long long i, int nb, int ne) {
         const int s = (int)(i % STAGES);
-        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long tile = first_tile + i * tile_step;
         long long r0, rend;
         tile_rows(tile, r0, rend);
         const int nr = (int)((rend - r0) < BLOCK ? (rend - r0) : BLOCK);
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         }
     };
     auto endpoints = [&](long long i, int& nb, int& ne) {
-        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long tile = first_tile + i * tile_step;
         long long r0, rend;
         tile_rows(tile, r0, rend);
         const long long r1 = (r0 + BLOCK < rend) ? r0 + BLOCK : rend;
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
             }
         }
         mbar_wait(&full[s], (unsigned)((i / STAGES) & 1));
-        const long long tile = blockIdx.x + i * (long long)gridDim.x;
+        const long long tile = first_tile + i * tile_step;
         long long r0, rend;
         tile_rows(tile, r0, rend);
         const int nr = (int)((rend - r0) < BLOCK ? (rend - r0) : BLOCK);
@@ -472,8 +483,14 @@ __global__ void __launch_bounds__(256) k_spmv_pat(PatArgs pa, SpmvArgs a, PkRedA
     // R rows per thread are in flight together (ids, epilogue operands and gathers of all R rows are independent):
     // this kernel moves ~20 bytes per row, so it needs thousands of rows in flight per SM to cover DRAM latency.
     constexpr int R = (FUSE == 0 && NV == 1) ? 4 : 2;
-    const long long stride = (long long)gridDim.x * 256;
-    for (long long t0 = (long long)blockIdx.x * 256 + threadIdx.x; t0 < na + nb; t0 += R * stride) {
+    // blocked assignment (see k_spmv_tma): block b owns rows [b*span, (b+1)*span), walked 256 at a time; the R rows a
+    // thread has in flight are 256 apart, i.e. consecutive sub-tiles of the same block
+    const long long total = na + nb;
+    const long long span = a.blocked ? ((total + gridDim.x - 1) / gridDim.x + 255) / 256 * 256 : 0;
+    const long long stride = a.blocked ? 256 : (long long)gridDim.x * 256;
+    const long long t_begin = a.blocked ? (long long)blockIdx.x * span + threadIdx.x : (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long t_end = a.blocked ? (((long long)blockIdx.x + 1) * span < total ? ((long long)blockIdx.x + 1) * span : total) : total;
+    for (long long t0 = t_begin; t0 < t_end; t0 += R * stride) {
         long long row[R];
         int sb[R], len[R];
         double wi[R], fa[R], fb[R], fx[R], xr[R], sum0[R], sum1[R];
@@ -481,7 +498,7 @@ __global__ void __launch_bounds__(256) k_spmv_pat(PatArgs pa, SpmvArgs a, PkRedA
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const long long t = t0 + r * stride;
-            const bool ok = t < na + nb;
+            const bool ok = t < t_end;
             row[r] = ok ? (t < na ? a.row_lo + t : a.row_lo2 + (t - na)) : -1;
             id[r] = ok ? (int)pa.id[row[r]] : 0;
         }
@@ -1031,6 +1048,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         static int ef = -1;
         if (ef < 0) { const char* e = getenv("PK_L2_HINT"); ef = e ? atoi(e) : 1; }
         a.evict_first = ef;
+        static int bl = -1;
+        if (bl < 0) { const char* e = getenv("PK_TILE_ORDER"); bl = (e && strcmp(e, "blocked") == 0) ? 1 : 0; }
+        a.blocked = bl;
     }
     a.reduce = (dots.w || (dots.fuse && dots.epi != EPI_KS_STEP)) ? 1 : 0;
     int grid = 0;
