@@ -382,7 +382,7 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
     if not 0 <= k <= _lib.PK_KMAX:
         raise PkError(f"k must be in 0..{_lib.PK_KMAX}")
     mid = _lib.METHOD_IDS[method]
-    hist_len = min(maxiter + k + 3, max(HIST_CAP, 4))
+    hist_len = max(4, min(maxiter + k + 3, HIST_CAP))
     residual = torch.zeros(hist_len, dtype=torch.float64, device=dev)
     nosl = torch.zeros(hist_len, dtype=torch.int64, device=dev)
     khist = torch.zeros(hist_len, dtype=torch.int64, device=dev) if method == "adaptivekskipmrr" else None
