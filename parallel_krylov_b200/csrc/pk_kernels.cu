@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <map>
+#include <tuple>
 
 namespace {
 
@@ -328,21 +329,23 @@ inline PkRedArgs red_args_n(pk_ctx* ctx, int epi, int nsums) {
 
 // ---------------------------------------------------------------------------------------------------------------
 int pk_blocks_per_sm(const void* kernel, int block, size_t smem) {
-    static std::map<std::pair<const void*, size_t>, int> cache;
-    static std::map<const void*, bool> opted_in;
-    if (smem > 40 * 1024 && !opted_in[kernel]) {
+    // caches are per (device, kernel): the opt-in attribute and the occupancy both belong to the current device
+    static std::map<std::tuple<int, const void*, size_t>, int> cache;
+    static std::map<std::pair<int, const void*>, bool> opted_in;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 40 * 1024 && !opted_in[{dev, kernel}]) {
         // opt in ONCE to the device maximum: the attribute is a ceiling for later launches, so it must never be lowered
-        int dev = 0, max_optin = 0;
-        cudaGetDevice(&dev);
+        int max_optin = 0;
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
         int stat = 1024;
         if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - stat) != cudaSuccess)
             cudaGetLastError();   // do not leave a stale error for the next launch check
-        opted_in[kernel] = true;
+        opted_in[{dev, kernel}] = true;
     }
-    auto key = std::make_pair(kernel, smem);
+    auto key = std::make_tuple(dev, kernel, smem);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     int per_sm = 0;
