@@ -417,6 +417,35 @@ def run_ours(args):
                                   f"serial csr_matvec + OpenBLAS dots), {ci['time']:.1f}s, timed like the reference"}
         log(f"[cpu_baseline] {cpu_baseline['value']:.4f} it/s ({time.perf_counter() - t_cpu:.1f}s total)")
 
+    # ---- the other single-GPU BASELINE.json configs, measured briefly in the same run (N=1, default workload only) ---
+    other = None
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_other:
+        other = {}
+        del h_rowptr, h_col, h_val, h_b, h_x
+        torch.cuda.empty_cache()
+        for name in ("mrr_p3d128", "kskipcg4_p3d256", "cg_p3d256"):
+            s2, k2, kind2, dims2, cap2 = WORKLOADS[name]
+            rp2, c2, v2, n2 = dp.stencil_csr(*dims2, ctx=ctx)
+            op2 = Operator.from_csr_tensors(rp2, c2, v2, n2, ctx)
+            b2 = dp.hash_normal(0, n2, ctx=ctx)
+            kw2 = {"k": k2} if k2 is not None else {}
+            solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
+            torch.cuda.synchronize()
+            e0.record()
+            its2 = 0
+            for _ in range(2):
+                _, i2 = solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
+                its2 += i2["iterations"]
+            e1.record()
+            torch.cuda.synchronize()
+            v_its = its2 / (e0.elapsed_time(e1) * 1e-3)
+            _, pib = algorithmic_bytes(s2, k2 or 0, n2, int(v2.numel()))
+            other[name] = {"iterations_per_s": v_its, "iterations_per_solve": its2 / 2,
+                           "frac_of_hbm_roofline": pib * v_its / 1e9 / peak,
+                           "workload": workload_config(name, n2, int(v2.numel()), cap2)["workload"]}
+            del op2, rp2, c2, v2, b2
+            torch.cuda.empty_cache()
+
     line = {
         "metric": "solver_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1),
@@ -427,6 +456,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_total),
                 "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "exposed_comm": exposed,
+        "other_baseline_configs": other,
     }
     emit(line)
     if world > 1:
@@ -454,6 +484,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--maxiter", type=int, default=0, help="override the per-step iteration cap")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the brief runs of the other BASELINE configs")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs in the timed region (no per-launch event timing of the SpMV kernel)")
     args = ap.parse_args()
