@@ -31,7 +31,6 @@ struct SpmvArgs {
     double* y0;
     double* y1;
     const double* w;        // fused dots against this vector (nullable)
-    int w_is_x;             // w == x0 (CG's p.Ap): take w[row] from the diagonal gather instead of loading it again
     long long row_lo, row_hi;
     long long row_lo2, row_hi2;   // optional second row range processed by the same launch (boundary rows above/below)
     // halo received by NVLink push: columns >= n_own read from the receive buffer after waiting for the peers' flags
@@ -60,7 +59,7 @@ struct SpmvArgs {
 template <int NV, int BLOCK, bool VEC>
 __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra) {
     if (pk_done(ra.st)) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sval = reinterpret_cast<double*>(smem_raw);              // [cap]
     int* scol = reinterpret_cast<int*>(sval + a.cap);                // [cap]
     __shared__ int rp[BLOCK + 1];
@@ -1037,7 +1036,6 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     SpmvArgs a;
     a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
     a.x0 = x; a.x1 = x1; a.y0 = y; a.y1 = y1; a.w = dots.w;
-    a.w_is_x = (dots.w == x) ? 1 : 0;
     a.fuse = dots.fuse; a.cj = dots.cj; a.f_a = dots.f_a; a.f_b = dots.f_b; a.f_x = dots.f_x; a.f_out = dots.f_out;
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
