@@ -39,6 +39,9 @@ bool pk_mat_can_fuse(const pk_mat* m);
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
 int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result);
 
+// pk_persistent.cu — whole CG loop as one cooperative kernel (small, L2-resident systems)
+int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double* p, double* v, int iters);
+
 // pk_comm.cu — NCCL over NVLink
 int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s);
 int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s);

@@ -368,8 +368,8 @@ struct Solve {
 
     // Enqueue `body` batches until the device reports the stop flag.  unit = solver iterations one body() adds.
     template <class Body>
-    int run_batches(long long unit, long long already, Body body) {
-        long long batch = o.check_every;
+    int run_batches(long long unit, long long already, Body body, long long force_batch = 0) {
+        long long batch = force_batch > 0 ? force_batch : o.check_every;
         if (batch <= 0) {
             // aim for >= ~0.5 ms of device work between polls (rough: 200 bytes per row per iteration at 6 TB/s)
             double per_it_us = std::max(8.0, (double)n * 200.0 / 6.0e6);
@@ -451,6 +451,18 @@ struct Solve {
         double *r = vec(0), *p = vec(1), *v = vec(2);
         PK_CHECK(initial_residual(r, p, v, EPI_CG_INIT));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        if (use_persistent()) {
+            // small system: the loop runs inside one cooperative kernel, `chunk` iterations per launch
+            const int chunk = 64;
+            Solve* self = this;
+            const bool graph_saved = o.use_graph != 0;
+            o.use_graph = 0;                                       // cooperative launches are not captured
+            int rc = run_batches(chunk, 0, [&]() -> int {
+                return pk_launch_cg_persistent(self->ctx, self->A, self->x, r, p, v, chunk);
+            }, 1);
+            o.use_graph = graph_saved ? 1 : 0;
+            return rc;
+        }
         PK_CHECK(run_batches(1, 0, [&]() -> int {
             PK_CHECK(apply(p, v, p, EPI_CG_ALPHA));               // v = A p ; sigma = p.v ; alpha
             PK_CHECK(pk_launch_cg_xr(ctx, n, x, r, p, v));        // x += alpha p ; r -= alpha v ; gamma' ; beta ; test
@@ -458,6 +470,17 @@ struct Solve {
             return PK_OK;
         }));
         return PK_OK;
+    }
+
+    // one cooperative kernel for the whole CG loop: single GPU, CSR, small enough to be latency-bound
+    bool use_persistent() const {
+        const char* e = getenv("PK_PERSISTENT");                   // 0: never, 1: whenever possible, unset: by size
+        const int mode = e ? atoi(e) : -1;
+        if (mode == 0 || ctx->n_ranks > 1 || A->kind == MAT_DENSE || A->distributed) return false;
+        if (mode == 1) return true;
+        // measured on B200 (graph replay vs persistent): 2-D 256^2 (65 k rows) 62.7 k -> 109 k it/s; 128^3 (2.1 M rows)
+        // 15.5 k vs 12.5 k it/s.  Below ~300 k rows the launches dominate, above the TMA-pipelined kernels win.
+        return A->n_rows <= 300000 && A->nnz <= 8000000;
     }
 
     // ---- MrR: /root/reference/v3/cpu/mrr.py:7-61 -------------------------------------------------------------

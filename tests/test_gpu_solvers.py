@@ -70,6 +70,25 @@ def test_solver_matches_reference_golden(pk, case):
         np.testing.assert_allclose(x, gold["x"], rtol=1e-6, atol=1e-8 * np.abs(gold["x"]).max())
 
 
+_CG_CASES = [c for c in CASES if c["solver"] == "cg" and c["maxiter"] is None and c["tol"] == 1e-8]
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("case", _CG_CASES, ids=[c["id"] for c in _CG_CASES])
+def test_cg_kernel_sequence_and_persistent_kernel_both_match_golden(pk, case, mode, monkeypatch):
+    """Small systems run CG as one cooperative persistent kernel by default; PK_PERSISTENT=0 forces the three-kernel
+    sequence the large systems use.  Both must reproduce the reference."""
+    monkeypatch.setenv("PK_PERSISTENT", mode)
+    gold = load(case)
+    mat, b, x, info = _run(pk, case)
+    assert abs(int(info["nosl"][-1]) - int(gold["nosl"][-1])) <= 2
+    m = min(50, len(info["residual"]), len(gold["residual"]))
+    np.testing.assert_allclose(info["residual"][:m], gold["residual"][:m], rtol=1e-10)
+    assert oracle.true_relres(mat, b, x) < 1e-8 * 1.001
+    if mode == "1" and not case["matrix"].startswith("dense"):     # dense A always takes the kernel sequence
+        assert info["gpu_launches"] < 40          # init kernels + one launch per 64 iterations
+
+
 def test_adaptive_guard_fires_and_lowers_k(pk):
     case = next(c for c in CASES if c["id"].startswith("adaptivekskipmrr_k16__p2d48"))
     mat, b, x, info = _run(pk, case)
