@@ -133,17 +133,12 @@ __global__ void __launch_bounds__(PB) k_cg_persistent(CgPersistArgs a) {
 
 // iterations per launch: `iters`.  Returns PK_ERR_UNSUPPORTED when the device cannot co-schedule the grid.
 int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double* p, double* v, int iters) {
-    static int grid_cache = 0;
-    if (grid_cache == 0) {
-        int coop = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        if (!coop) return PK_ERR_UNSUPPORTED;
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent, PB, 0) != cudaSuccess || per_sm < 1)
-            return PK_ERR_UNSUPPORTED;
-        if (per_sm > 4) per_sm = 4;        // a barrier over fewer blocks is cheaper; the work is latency-bound anyway
-        grid_cache = ctx->sm_count * per_sm;
-    }
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (!coop) return PK_ERR_UNSUPPORTED;
+    int per_sm = pk_blocks_per_sm((const void*)k_cg_persistent, PB, 0);   // cached per device
+    if (per_sm > 4) per_sm = 4;            // a barrier over fewer blocks is cheaper; the work is latency-bound anyway
+    const int grid_cache = ctx->sm_count * per_sm;
     long long want = (m->n_rows + PB - 1) / PB;
     int grid = (int)(want < grid_cache ? (want < 1 ? 1 : want) : grid_cache);
     if (2 * grid > ctx->red.max_blocks * PK_MAX_SUMS) return PK_ERR_UNSUPPORTED;
