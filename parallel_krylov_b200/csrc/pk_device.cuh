@@ -2,6 +2,7 @@
 // (every scalar recurrence of the reference loops, executed by one thread on the reduced sums).
 #pragma once
 #include "pk_common.cuh"
+#include "pk_scalars.h"
 
 // ---- TMA bulk-copy / mbarrier primitives (sm_90+; SASS: UBLKCP, SYNCS.*) --------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -93,66 +94,9 @@ __device__ __forceinline__ void pk_stop_test(PkState* st, double res) {
     }
 }
 
-// All k+1 (alpha_j, beta_j) of a k-skip CG trip from the Gram sums — v3/cpu/kskipcg.py:51-52, :59-68.
-__device__ inline void pk_kskipcg_scalars(PkState* st) {
-    const int k = st->k;
-    const double* G = st->gram;
-    double a[2 * PK_KMAX + 2], f[2 * PK_KMAX + 4], c[2 * PK_KMAX + 2];
-    for (int j = 0; j < 2 * k + 1; ++j) a[j] = G[6 * (j >> 1) + (j & 1)];
-    a[2 * k + 1] = 0.0;
-    for (int j = 0; j < 2 * k + 4; ++j) f[j] = G[6 * (j >> 1) + 4 + (j & 1)];
-    for (int j = 0; j < 2 * k + 2; ++j) c[j] = G[6 * (j >> 1) + 2 + (j & 1)];
-    double alpha = a[0] / f[1];
-    double beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
-    st->coef[0] = alpha;
-    st->coef[1] = beta;
-    for (int j = 0; j < k; ++j) {
-        for (int l = 0; l < 2 * (k - j) + 1; ++l) {
-            a[l] = a[l] + alpha * (alpha * f[l + 2] - 2.0 * c[l + 1]);
-            double d = c[l] - alpha * f[l + 1];
-            c[l] = a[l] + d * beta;
-            f[l] = c[l] + beta * (d + beta * f[l]);
-        }
-        alpha = a[0] / f[1];
-        beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
-        st->coef[2 * (j + 1)] = alpha;
-        st->coef[2 * (j + 1) + 1] = beta;
-    }
-}
-
-// All k+1 (zeta_j, eta_j) of a k-skip MrR trip — v3/cpu/kskipmrr.py:62-64, :72-88.
-__device__ inline void pk_kskipmrr_scalars(PkState* st) {
-    const int k = st->k;
-    const double* G = st->gram;
-    double al[2 * PK_KMAX + 3], be[2 * PK_KMAX + 2], de[2 * PK_KMAX + 1];
-    for (int j = 0; j < 2 * k + 3; ++j) al[j] = G[6 * (j >> 1) + (j & 1)];
-    be[0] = 0.0;
-    for (int j = 1; j < 2 * k + 2; ++j) be[j] = G[6 * (j >> 1) + 2 + (j & 1)];
-    for (int j = 0; j < 2 * k + 1; ++j) de[j] = G[6 * (j >> 1) + 4 + (j & 1)];
-    double d = al[2] * de[0] - be[1] * be[1];
-    double zeta = (al[1] * de[0]) / d;
-    double eta = ((-al[1]) * be[1]) / d;
-    st->coef[0] = zeta;
-    st->coef[1] = eta;
-    for (int j = 0; j < k; ++j) {
-        de[0] = (zeta * zeta) * al[2] + (eta * zeta) * be[1];
-        al[0] = al[0] - zeta * al[1];
-        de[1] = ((eta * eta) * de[1] + ((2.0 * eta) * zeta) * be[2]) + (zeta * zeta) * al[3];
-        be[1] = (eta * be[1] + zeta * al[2]) - de[1];
-        al[1] = -be[1];
-        for (int l = 2; l < 2 * (k - j) + 1; ++l) {
-            de[l] = ((eta * eta) * de[l] + ((2.0 * eta) * zeta) * be[l + 1]) + (zeta * zeta) * al[l + 2];
-            double tau = eta * be[l] + zeta * al[l + 1];
-            be[l] = tau - de[l];
-            al[l] = al[l] - (tau + be[l]);
-        }
-        d = al[2] * de[0] - be[1] * be[1];
-        zeta = (al[1] * de[0]) / d;
-        eta = ((-al[1]) * be[1]) / d;
-        st->coef[2 * (j + 1)] = zeta;
-        st->coef[2 * (j + 1) + 1] = eta;
-    }
-}
+// The O(k^2) k-skip recurrences live in pk_scalars.h (plain C++, also compiled for the host by the CPU tests).
+__device__ inline void pk_kskipcg_scalars(PkState* st) { pk_kskipcg_coef(st->gram, st->k, st->coef); }
+__device__ inline void pk_kskipmrr_scalars(PkState* st) { pk_kskipmrr_coef(st->gram, st->k, st->coef); }
 
 // The scalar engine.  `st->red` (or st->gram) already holds the fully reduced sums.
 template <bool GRAM>
