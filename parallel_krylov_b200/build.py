@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libpkrylov.so")
 SOURCES = ["pk_kernels.cu", "pk_spmv.cu", "pk_solvers.cu", "pk_comm.cu", "pk_generators.cu", "pk_persistent.cu"]
-HEADERS = ["pk_common.cuh", "pk_device.cuh", "pk_scalars.h", "pk_launch.h", os.path.join(ROOT, "include", "pkrylov.h")]
+HEADERS = ["pk_common.cuh", "pk_device.cuh", "pk_scalars.h", "pk_state.h", "pk_launch.h", os.path.join(ROOT, "include", "pkrylov.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -32,59 +32,7 @@ void pk_set_error(const char* fmt, ...);
         }                                                            \
     } while (0)
 
-// ---------------------------------------------------------------------------------------------------------------
-// device-resident solver state: every scalar of the reference loops lives here, so no iteration needs the host.
-constexpr int PK_MAX_SUMS = 64;                      // sums one reducing kernel may produce
-constexpr int PK_GRAM_MAX = 6 * (PK_KMAX + 2) + 8;   // Gram buffer entries
-
-struct PkState {
-    // control
-    int done;             // 1: every later kernel of the stream is a no-op (stopping rule already fired)
-    int converged;        // isConverged
-    int guard;            // adaptive: residual grew (host handles the rollback)
-    int pad0;
-    long long it;         // `i` of the reference loops (number of solution updates)
-    long long idx;        // `index` (history position); == it for cg/mrr
-    long long maxiter;
-    double tol;
-    double bnorm;         // ||b||
-    // cg / mrr scalars
-    double gamma, alpha, beta, zeta, eta, mu, nu;
-    double rr;            // ||r||^2 of the newest residual
-    // k-skip: coefficient pairs of the k+1 steps of one trip: (alpha_j, beta_j) or (zeta_j, eta_j)
-    double coef[2 * (PK_KMAX + 1)];
-    double gram[PK_GRAM_MAX];
-    // reduced sums of the last reducing kernel (multi-GPU: all-reduced in place, then the scalar kernel runs)
-    double red[PK_MAX_SUMS];
-    // history (device arrays owned by the caller)
-    double* res;
-    long long* nosl;
-    long long* khist;
-    int k;                // current k (adaptive)
-    int pad1;
-    long long hist_len;   // capacity of res/nosl/khist: entries beyond it are dropped, never written
-};
-
-// scalar epilogues ("scalar engine"): run by ONE thread on the fully reduced sums.
-enum PkEpi : int {
-    EPI_NONE = 0,        // sums -> st->red only
-    EPI_BNORM,           // red[0] = b.b            -> bnorm
-    EPI_CG_INIT,         // red[0] = r.r            -> gamma, res[0], stop test
-    EPI_CG_ALPHA,        // red[0] = p.Ap           -> alpha = gamma / sigma
-    EPI_CG_BETA,         // red[0] = r.r            -> beta, gamma, it++, res[it], stop test
-    EPI_RES0,            // red[0] = r.r            -> res[0] (mrr family: no stop test before the first step)
-    EPI_MRR_FIRST,       // red[0] = r.Ar, red[1] = Ar.Ar -> zeta
-    EPI_MRR_STEP,        // red[0] = r.r            -> it++, res[it], stop test   (cg/mrr style: idx == it)
-    EPI_MRR_GAMMA,       // red[0] = y.Ar, red[2] = y.y -> gamma(nu/mu)
-    EPI_MRR_ZETA,        // red[0] = r.s, red[1] = s.s -> zeta, eta
-    EPI_KS_FIRST,        // like EPI_MRR_STEP for the opening step of the k-skip MrR family (it=idx=1)
-    EPI_KS_TRIP_END,     // red[0] = r.r            -> it += k+1, idx++, res[idx], stop test
-    EPI_KS_STEP,         // (no scalar work; intermediate steps of a trip)
-    EPI_GRAM_CG,         // gram[] complete         -> coef[] = (alpha_j, beta_j)
-    EPI_GRAM_MRR,        // gram[] complete         -> coef[] = (zeta_j, eta_j)
-    EPI_GRAM_PART,       // a Gram window that is not the last: copy sums into gram[] only
-    EPI_ADAPT_STEP,      // adaptive rollback step: it++, idx++, res[idx]  (no stop test; host lowers k)
-};
+#include "pk_state.h"
 
 struct PkReduce {           // scratch for the deterministic two-stage reductions
     double* partials;       // [PK_MAX_SUMS][max_blocks]

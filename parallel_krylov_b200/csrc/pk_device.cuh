@@ -72,120 +72,7 @@ struct PkRedArgs {
 // Rounding discipline: the library is compiled with -fmad=false so that a*b+c rounds twice exactly like numpy's
 // temporaries (`x += alpha * p` is a multiply then an add, /root/reference/v3/cpu/cg.py:30).
 
-__device__ __forceinline__ void pk_record(PkState* st, long long idx, long long it, double res, bool with_k) {
-    if (idx < st->hist_len) {
-        st->res[idx] = res;
-        st->nosl[idx] = it;
-        if (with_k && st->khist) st->khist[idx] = st->k;
-    }
-}
-
-__device__ __forceinline__ void pk_stop_test(PkState* st, double res) {
-    // `while i < maxiter:` is evaluated before `if residual[i] < tol` (v3/cpu/cg.py:19-24): reaching the cap ends
-    // the loop as "not converged" even when the last residual is below tol.
-    if (st->it < st->maxiter) {
-        if (res < st->tol) {
-            st->converged = 1;
-            st->done = 1;
-        }
-    } else {
-        st->converged = 0;
-        st->done = 1;
-    }
-}
-
-// The O(k^2) k-skip recurrences live in pk_scalars.h (plain C++, also compiled for the host by the CPU tests).
-__device__ inline void pk_kskipcg_scalars(PkState* st) { pk_kskipcg_coef(st->gram, st->k, st->coef); }
-__device__ inline void pk_kskipmrr_scalars(PkState* st) { pk_kskipmrr_coef(st->gram, st->k, st->coef); }
-
-// The scalar engine.  `st->red` (or st->gram) already holds the fully reduced sums.
-template <bool GRAM>
-__device__ inline void pk_epilogue(int epi, PkState* st) {
-    const double* s = st->red;
-    switch (epi) {
-        case EPI_BNORM:
-            st->bnorm = sqrt(s[0]);
-            break;
-        case EPI_CG_INIT: {               // v3/cpu/cg.py:14, :21-24 (first pass)
-            st->gamma = s[0];
-            st->rr = s[0];
-            double res = sqrt(s[0]) / st->bnorm;
-            st->it = 0;
-            st->idx = 0;
-            pk_record(st, 0, 0, res, false);
-            pk_stop_test(st, res);
-            break;
-        }
-        case EPI_CG_ALPHA:                // v3/cpu/cg.py:28-29
-            st->alpha = st->gamma / s[0];
-            break;
-        case EPI_CG_BETA: {               // v3/cpu/cg.py:32-37, then :21-24 of the next pass
-            double g = s[0];
-            st->beta = g / st->gamma;
-            st->gamma = g;
-            st->rr = g;
-            st->it += 1;
-            st->idx = st->it;
-            double res = sqrt(g) / st->bnorm;
-            pk_record(st, st->it, st->it, res, false);
-            pk_stop_test(st, res);
-            break;
-        }
-        case EPI_RES0: {                  // v3/cpu/mrr.py:13 — recorded, not tested
-            st->rr = s[0];
-            st->it = 0;
-            st->idx = 0;
-            pk_record(st, 0, 0, sqrt(s[0]) / st->bnorm, true);
-            break;
-        }
-        case EPI_MRR_FIRST:               // v3/cpu/mrr.py:19   zeta = (r.Ar)/(Ar.Ar)
-            st->zeta = s[0] / s[1];
-            break;
-        case EPI_KS_FIRST:                // opening step done: i = 1, index = 1 (v3/cpu/mrr.py:24-25, kskipmrr.py:32-34)
-        case EPI_MRR_STEP: {              // v3/cpu/mrr.py:49-50 then :30-33
-            st->rr = s[0];
-            st->it += 1;
-            st->idx = st->it;
-            double res = sqrt(s[0]) / st->bnorm;
-            pk_record(st, st->it, st->it, res, true);
-            pk_stop_test(st, res);
-            break;
-        }
-        case EPI_MRR_GAMMA:               // v3/cpu/mrr.py:37-39  mu = y.y, nu = y.Ar
-            st->nu = s[0];
-            st->mu = s[2];
-            st->gamma = s[0] / s[2];
-            break;
-        case EPI_MRR_ZETA:                // v3/cpu/mrr.py:41-44
-            st->zeta = s[0] / s[1];
-            st->eta = (-st->zeta) * st->gamma;
-            break;
-        case EPI_KS_TRIP_END: {           // v3/cpu/kskipcg.py:74-76 / kskipmrr.py:95-97, then the loop-top test
-            st->rr = s[0];
-            st->it += st->k + 1;
-            st->idx += 1;
-            double res = sqrt(s[0]) / st->bnorm;
-            pk_record(st, st->idx, st->it, res, true);
-            pk_stop_test(st, res);
-            break;
-        }
-        case EPI_ADAPT_STEP: {            // v3/cpu/adaptivekskipmrr.py:58-61 (rollback step; host lowers k)
-            st->rr = s[0];
-            st->it += 1;
-            st->idx += 1;
-            pk_record(st, st->idx, st->it, sqrt(s[0]) / st->bnorm, false);
-            break;
-        }
-        case EPI_GRAM_CG:
-            if (GRAM) pk_kskipcg_scalars(st);   // only the Gram kernel / scalar kernel carry the recurrence stack
-            break;
-        case EPI_GRAM_MRR:
-            if (GRAM) pk_kskipmrr_scalars(st);
-            break;
-        default:
-            break;
-    }
-}
+// pk_record / pk_stop_test / pk_epilogue (the scalar engine) live in pk_state.h: plain C++ shared with the host tests.
 
 // --------------------------------------------------------------------------------------------------------------
 // Block reduction of NS running sums (fixed shape: shuffle tree, then warps in order), one partial per block,

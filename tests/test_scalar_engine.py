@@ -87,3 +87,152 @@ def test_kskipcg_coefficients_bitwise(host_lib, k):
     coef = np.zeros(2 * (k + 1))
     host_lib.host_kskipcg_coef(G.ctypes.data, k, coef.ctypes.data)
     assert np.array_equal(coef, np.array(want, dtype=np.float64).ravel())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole solves on the CPU: numpy does the vector work in the order the CUDA kernels do it, every scalar, the history
+# and the stopping rule go through the device's own scalar engine (pk_state.h, host build).  Must equal the oracle —
+# and therefore the reference — bit for bit, entry for entry.
+import re
+
+_SRC = open(os.path.join(HERE, "..", "parallel_krylov_b200", "csrc", "pk_state.h")).read()
+_ENUM = re.search(r"enum PkEpi : int \{(.*?)\};", _SRC, flags=re.S).group(1)
+EPI = {}
+_next = 0
+for _name, _val in re.findall(r"^\s*(EPI_[A-Z_0-9]+)(?:\s*=\s*(\d+))?\s*,", _ENUM, flags=re.M):
+    _next = int(_val) if _val else _next
+    EPI[_name] = _next
+    _next += 1
+ALPHA, BETA, GAMMA, ZETA, ETA, DONE, CONV, IT, IDX, COEF = range(10)
+
+
+class Engine:
+    def __init__(self, lib, maxiter, tol, k=0, with_khist=False):
+        for fn, res, args in ((lib.hs_new, C.c_void_p, [C.c_longlong, C.c_double, C.c_int, C.c_longlong, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p]),
+                              (lib.hs_free, None, [C.c_void_p]),
+                              (lib.hs_epilogue, None, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+                              (lib.hs_gram, None, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+                              (lib.hs_get, C.c_double, [C.c_void_p, C.c_int, C.c_int])):
+            fn.restype, fn.argtypes = res, args
+        self.lib = lib
+        n = maxiter + k + 3
+        self.res = np.zeros(n)
+        self.nosl = np.zeros(n, dtype=np.int64)
+        self.khist = np.zeros(n, dtype=np.int64) if with_khist else None
+        self.st = lib.hs_new(maxiter, tol, k, n, self.res.ctypes.data, self.nosl.ctypes.data,
+                             self.khist.ctypes.data if with_khist else None)
+
+    def epi(self, name, *sums):
+        s = np.array(sums, dtype=np.float64)
+        self.lib.hs_epilogue(self.st, EPI[name], s.ctypes.data, len(s))
+
+    def gram(self, name, G):
+        G = np.ascontiguousarray(G)
+        self.lib.hs_gram(self.st, EPI[name], G.ctypes.data, len(G))
+
+    def get(self, what, j=0):
+        return self.lib.hs_get(self.st, what, j)
+
+    def history(self):
+        m = int(self.get(IDX)) + 1
+        return self.res[:m].copy(), self.nosl[:m].copy()
+
+
+def _emulate(lib, solver, A, b, tol, maxiter, k=0):
+    """The launch sequence of csrc/pk_solvers.cu with numpy standing in for the vector kernels."""
+    n = b.size
+    x = np.zeros(n)
+    e = Engine(lib, maxiter, tol, k)
+    e.epi("EPI_BNORM", np.dot(b, b))
+    if solver == "cg":
+        r = b - A.dot(x); p = r.copy()
+        e.epi("EPI_CG_INIT", np.dot(r, r))
+        while not e.get(DONE):
+            v = A.dot(p)
+            e.epi("EPI_CG_ALPHA", np.dot(p, v), np.dot(v, v), np.dot(p, p))
+            al = e.get(ALPHA)
+            x = x + al * p
+            r = r - al * v
+            e.epi("EPI_CG_BETA", np.dot(r, r))
+            p = r + e.get(BETA) * p
+    elif solver == "mrr":
+        r = b - A.dot(x)
+        e.epi("EPI_RES0", np.dot(r, r))
+        ar = A.dot(r)
+        e.epi("EPI_MRR_FIRST", np.dot(r, ar), np.dot(ar, ar), np.dot(r, r))
+        ze = e.get(ZETA)
+        y = ze * ar; z = (-ze) * r; r = r - y; x = x - z
+        e.epi("EPI_KS_FIRST", np.dot(r, r))
+        while not e.get(DONE):
+            ar = A.dot(r)
+            e.epi("EPI_MRR_GAMMA", np.dot(y, ar), np.dot(ar, ar), np.dot(y, y))
+            s = ar - e.get(GAMMA) * y
+            e.epi("EPI_MRR_ZETA", np.dot(r, s), np.dot(s, s))
+            ze, et = e.get(ZETA), e.get(ETA)
+            y = et * y + ze * ar
+            z = et * z - ze * r
+            r = r - y
+            x = x - z
+            e.epi("EPI_MRR_STEP", np.dot(r, r))
+    elif solver == "kskipcg":
+        Ar = np.zeros((k + 1, n)); Ap = np.zeros((k + 2, n))
+        Ar[0] = b - A.dot(x); Ap[0] = Ar[0]
+        e.epi("EPI_CG_INIT", np.dot(Ar[0], Ar[0]))
+        Ap[1] = A.dot(Ap[0])
+        while not e.get(DONE):
+            for j in range(1, k + 1):                      # two-chain pass
+                Ar[j] = A.dot(Ar[j - 1]); Ap[j + 1] = A.dot(Ap[j])
+            e.gram("EPI_GRAM_CG", _gram_layout(1, Ar, Ap, k))
+            for j in range(k + 1):
+                al, be = e.get(COEF, 2 * j), e.get(COEF, 2 * j + 1)
+                x = x + al * Ap[0]
+                Ar[0] = Ar[0] - al * Ap[1]
+                Ap[0] = Ar[0] + be * Ap[0]
+                if j == k:
+                    e.epi("EPI_KS_TRIP_END", np.dot(Ar[0], Ar[0]))
+                Ap[1] = A.dot(Ap[0])
+    elif solver == "kskipmrr":
+        Ar = np.zeros((k + 2, n)); Ay = np.zeros((k + 1, n))
+        Ar[0] = b - A.dot(x)
+        e.epi("EPI_RES0", np.dot(Ar[0], Ar[0]))
+        Ar[1] = A.dot(Ar[0])
+        e.epi("EPI_MRR_FIRST", np.dot(Ar[0], Ar[1]), np.dot(Ar[1], Ar[1]), np.dot(Ar[0], Ar[0]))
+        ze = e.get(ZETA)
+        Ay[0] = ze * Ar[1]; z = (-ze) * Ar[0]; Ar[0] = Ar[0] - Ay[0]; x = x - z
+        e.epi("EPI_KS_FIRST", np.dot(Ar[0], Ar[0]))
+        Ar[1] = A.dot(Ar[0])
+        while not e.get(DONE):
+            for j in range(1, k + 1):
+                Ar[j + 1] = A.dot(Ar[j]); Ay[j] = A.dot(Ay[j - 1])
+            e.gram("EPI_GRAM_MRR", _gram_layout(0, Ar, Ay, k))
+            for j in range(k + 1):
+                ze, et = e.get(COEF, 2 * j), e.get(COEF, 2 * j + 1)
+                Ay[0] = et * Ay[0] + ze * Ar[1]
+                z = et * z - ze * Ar[0]
+                Ar[0] = Ar[0] - Ay[0]
+                x = x - z
+                if j == k:
+                    e.epi("EPI_KS_TRIP_END", np.dot(Ar[0], Ar[0]))
+                Ar[1] = A.dot(Ar[0])
+    res, nosl = e.history()
+    out = {"residual": res, "nosl": nosl, "converged": bool(e.get(CONV))}
+    lib.hs_free(e.st)
+    return x, out
+
+
+@pytest.mark.parametrize("solver,k,cap", [("cg", 0, None), ("cg", 0, 17), ("mrr", 0, None), ("mrr", 0, 9),
+                                          ("kskipcg", 0, None), ("kskipcg", 3, None), ("kskipcg", 4, 22),
+                                          ("kskipmrr", 0, None), ("kskipmrr", 2, None), ("kskipmrr", 8, None),
+                                          ("kskipmrr", 4, 22)])
+def test_device_scalar_engine_drives_whole_solves_bitwise(host_lib, solver, k, cap):
+    A = problems.to_scipy(*problems.poisson3d(9, 8, 7))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    maxiter = A.shape[0] if cap is None else cap
+    kw = {"k": k} if solver.startswith("kskip") else {}
+    xo, io = oracle.SOLVERS[solver](A, b.copy(), tol=1e-8, maxiter=maxiter, **kw)
+    x, info = _emulate(host_lib, solver, A, b, 1e-8, maxiter, k)
+    assert np.array_equal(info["nosl"], io["nosl"])
+    assert np.array_equal(info["residual"], io["residual"])
+    assert np.array_equal(x, xo)
+    assert info["converged"] == io["converged"]
