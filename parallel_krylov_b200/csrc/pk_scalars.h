@@ -14,6 +14,17 @@
 #define PK_KMAX 32
 #endif
 
+// Squares.  The reference writes `zeta ** 2` on numpy float64 scalars, which goes through libm pow(); glibc's pow is
+// accurate to < 1 ulp but not correctly rounded, so about one square in 10^4 differs from the correctly rounded product
+// by one ulp.  The device multiplies (deterministic, correctly rounded).  The CPU tests also build this header with
+// -DPK_SQUARE_WITH_LIBM_POW to show that this is the ONLY difference to the oracle (bit-identical solves with it).
+#ifdef PK_SQUARE_WITH_LIBM_POW
+#include <math.h>
+#define PK_SQ(x) pow((x), 2.0)
+#else
+#define PK_SQ(x) ((x) * (x))
+#endif
+
 // Gram layout (see pkrylov.h: pk_gram): G[6*jj + t], t = {U[jj].U[jj], U[jj].U[jj+1], U[jj].V[jj],
 // (MrR: V[jj].U[jj+1] | CG: U[jj].V[jj+1]), V[jj].V[jj], V[jj].V[jj+1]}.
 
@@ -25,7 +36,7 @@ PK_HD inline void pk_kskipcg_coef(const double* G, int k, double* coef) {
     for (int j = 0; j < 2 * k + 4; ++j) f[j] = G[6 * (j >> 1) + 4 + (j & 1)];
     for (int j = 0; j < 2 * k + 2; ++j) c[j] = G[6 * (j >> 1) + 2 + (j & 1)];
     double alpha = a[0] / f[1];
-    double beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
+    double beta = (PK_SQ(alpha) * f[2]) / a[0] - 1.0;
     coef[0] = alpha;
     coef[1] = beta;
     for (int j = 0; j < k; ++j) {
@@ -36,7 +47,7 @@ PK_HD inline void pk_kskipcg_coef(const double* G, int k, double* coef) {
             f[l] = c[l] + beta * (d + beta * f[l]);
         }
         alpha = a[0] / f[1];
-        beta = ((alpha * alpha) * f[2]) / a[0] - 1.0;
+        beta = (PK_SQ(alpha) * f[2]) / a[0] - 1.0;
         coef[2 * (j + 1)] = alpha;
         coef[2 * (j + 1) + 1] = beta;
     }
@@ -49,24 +60,24 @@ PK_HD inline void pk_kskipmrr_coef(const double* G, int k, double* coef) {
     be[0] = 0.0;
     for (int j = 1; j < 2 * k + 2; ++j) be[j] = G[6 * (j >> 1) + 2 + (j & 1)];
     for (int j = 0; j < 2 * k + 1; ++j) de[j] = G[6 * (j >> 1) + 4 + (j & 1)];
-    double d = al[2] * de[0] - be[1] * be[1];
+    double d = al[2] * de[0] - PK_SQ(be[1]);
     double zeta = (al[1] * de[0]) / d;
     double eta = ((-al[1]) * be[1]) / d;
     coef[0] = zeta;
     coef[1] = eta;
     for (int j = 0; j < k; ++j) {
-        de[0] = (zeta * zeta) * al[2] + (eta * zeta) * be[1];
+        de[0] = PK_SQ(zeta) * al[2] + (eta * zeta) * be[1];
         al[0] = al[0] - zeta * al[1];
-        de[1] = ((eta * eta) * de[1] + ((2.0 * eta) * zeta) * be[2]) + (zeta * zeta) * al[3];
+        de[1] = (PK_SQ(eta) * de[1] + ((2.0 * eta) * zeta) * be[2]) + PK_SQ(zeta) * al[3];
         be[1] = (eta * be[1] + zeta * al[2]) - de[1];
         al[1] = -be[1];
         for (int l = 2; l < 2 * (k - j) + 1; ++l) {
-            de[l] = ((eta * eta) * de[l] + ((2.0 * eta) * zeta) * be[l + 1]) + (zeta * zeta) * al[l + 2];
+            de[l] = (PK_SQ(eta) * de[l] + ((2.0 * eta) * zeta) * be[l + 1]) + PK_SQ(zeta) * al[l + 2];
             double tau = eta * be[l] + zeta * al[l + 1];
             be[l] = tau - de[l];
             al[l] = al[l] - (tau + be[l]);
         }
-        d = al[2] * de[0] - be[1] * be[1];
+        d = al[2] * de[0] - PK_SQ(be[1]);
         zeta = (al[1] * de[0]) / d;
         eta = ((-al[1]) * be[1]) / d;
         coef[2 * (j + 1)] = zeta;

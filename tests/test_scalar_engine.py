@@ -14,16 +14,27 @@ from parallel_krylov_b200 import problems
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def host_lib(tmp_path_factory):
-    out = tmp_path_factory.mktemp("hostscalars") / "libhostscalars.so"
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(out),
+def _build(tmp_path_factory, name, extra):
+    out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", *extra, "-o", str(out),
                     os.path.join(HERE, "host_scalars.cpp")], check=True)
     lib = C.CDLL(str(out))
     for fn in (lib.host_kskipcg_coef, lib.host_kskipmrr_coef):
         fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         fn.restype = None
     return lib
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    """The scalar engine exactly as the device compiles it (squares are products)."""
+    return _build(tmp_path_factory, "hostscalars", [])
+
+
+@pytest.fixture(scope="module")
+def host_lib_pow(tmp_path_factory):
+    """Same source, squares through libm pow() like the reference's `x ** 2` on numpy scalars."""
+    return _build(tmp_path_factory, "hostscalarspow", ["-DPK_SQUARE_WITH_LIBM_POW", "-fno-builtin"])   # gcc folds pow(x, 2.0) into x*x otherwise
 
 
 def _gram_layout(mode, U, V, k):
@@ -236,3 +247,114 @@ def test_device_scalar_engine_drives_whole_solves_bitwise(host_lib, solver, k, c
     assert np.array_equal(info["residual"], io["residual"])
     assert np.array_equal(x, xo)
     assert info["converged"] == io["converged"]
+
+
+def _emulate_adaptive(lib, A, b, tol, maxiter, k0):
+    """Solve::adaptive() of csrc/pk_solvers.cu restated: the device engine keeps the history, the host reads one
+    residual per trip, applies the residual-growth guard, rolls back and lowers k."""
+    n = b.size
+    x = np.zeros(n)
+    e = Engine(lib, maxiter, tol, k0, with_khist=True)
+    lib.hs_set_k.argtypes = [C.c_void_p, C.c_int]
+    k = k0
+    Ar = np.zeros((k0 + 2, n)); Ay = np.zeros((k0 + 1, n))
+    e.epi("EPI_BNORM", np.dot(b, b))
+    bnorm = np.sqrt(np.dot(b, b))
+    Ar[0] = b - A.dot(x)
+    rr = np.dot(Ar[0], Ar[0])
+    e.epi("EPI_RES0", rr)
+    best_res = np.sqrt(rr) / bnorm
+    best_x = None
+
+    def opening(epi_name):
+        nonlocal x, z, rr
+        Ar[1] = A.dot(Ar[0])
+        e.epi("EPI_MRR_FIRST", np.dot(Ar[0], Ar[1]), np.dot(Ar[1], Ar[1]), np.dot(Ar[0], Ar[0]))
+        ze = e.get(ZETA)
+        Ay[0] = ze * Ar[1]; z = (-ze) * Ar[0]; Ar[0] = Ar[0] - Ay[0]; x = x - z
+        rr = np.dot(Ar[0], Ar[0])
+        e.epi(epi_name, rr)
+        Ar[1] = A.dot(Ar[0])
+
+    z = None
+    opening("EPI_KS_FIRST")
+    converged = False
+    while True:
+        if e.get(DONE) and not e.get(CONV):
+            break
+        if e.get(IT) >= maxiter:
+            break
+        res = np.sqrt(rr) / bnorm
+        if res > best_res:
+            x = best_x.copy()
+            Ar[0] = b - A.dot(x)
+            opening("EPI_ADAPT_STEP")
+            if k > 1:
+                k -= 1
+            lib.hs_set_k(e.st, k)
+            e.khist[int(e.get(IDX))] = k
+            res = np.sqrt(rr) / bnorm
+        else:
+            best_res = res
+            best_x = x.copy()
+        if res < tol:
+            converged = True
+            break
+        for j in range(1, k + 1):
+            Ar[j + 1] = A.dot(Ar[j]); Ay[j] = A.dot(Ay[j - 1])
+        e.gram("EPI_GRAM_MRR", _gram_layout(0, Ar[: k + 2], Ay[: k + 1], k))
+        for j in range(k + 1):
+            ze, et = e.get(COEF, 2 * j), e.get(COEF, 2 * j + 1)
+            Ay[0] = et * Ay[0] + ze * Ar[1]
+            z = et * z - ze * Ar[0]
+            Ar[0] = Ar[0] - Ay[0]
+            x = x - z
+            if j == k:
+                rr = np.dot(Ar[0], Ar[0])
+                e.epi("EPI_KS_TRIP_END", rr)
+            Ar[1] = A.dot(Ar[0])
+    m = int(e.get(IDX)) + 1
+    out = {"residual": e.res[:m].copy(), "nosl": e.nosl[:m].copy(), "khistory": e.khist[:m].copy(),
+           "converged": converged}
+    lib.hs_free(e.st)
+    return x, out
+
+
+@pytest.mark.parametrize("k,n2d", [(4, 24), (12, 48), (16, 48)])
+def test_adaptive_guard_logic_bitwise(host_lib_pow, k, n2d):
+    """The rollback / k-lowering flow (guard fires for k >= 10 on these systems) against the oracle, bit for bit.
+    These runs are chaotic (k >= 10), so the build that squares with libm pow() like the reference is used: with it
+    even the 372-iteration k=16 run with seven rollbacks is reproduced exactly."""
+    host_lib = host_lib_pow
+    A = problems.to_scipy(*problems.poisson2d(n2d))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    xo, io = oracle.adaptivekskipmrr(A, b.copy(), tol=1e-8, maxiter=2000, k=k)
+    x, info = _emulate_adaptive(host_lib, A, b, 1e-8, 2000, k)
+    assert np.array_equal(info["nosl"], io["nosl"])
+    assert np.array_equal(info["khistory"], io["khistory"])
+    assert np.array_equal(info["residual"], io["residual"])
+    assert np.array_equal(x, xo)
+    if k >= 12:
+        assert io["khistory"][-1] < k          # the guard really fired in this case
+
+
+def test_product_and_pow_squares_differ_by_at_most_one_ulp(host_lib, host_lib_pow):
+    """x*x (device) vs pow(x, 2) (reference): the coefficient sequences of a trip agree to ~1 ulp per square."""
+    A = problems.to_scipy(*problems.poisson3d(10, 9, 8))
+    n = A.shape[0]
+    worst = 0.0
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        k = 6
+        Ar = np.zeros((k + 2, n)); Ay = np.zeros((k + 1, n))
+        Ar[0] = rng.standard_normal(n); Ay[0] = 0.1 * rng.standard_normal(n)
+        for j in range(1, k + 2):
+            Ar[j] = A.dot(Ar[j - 1])
+        for j in range(1, k + 1):
+            Ay[j] = A.dot(Ay[j - 1])
+        G = _gram_layout(0, Ar, Ay, k)
+        c1, c2 = np.zeros(2 * (k + 1)), np.zeros(2 * (k + 1))
+        host_lib.host_kskipmrr_coef(G.ctypes.data, k, c1.ctypes.data)
+        host_lib_pow.host_kskipmrr_coef(G.ctypes.data, k, c2.ctypes.data)
+        worst = max(worst, float(np.max(np.abs(c1 - c2) / np.abs(c2))))
+    assert worst < 1e-9        # the recurrence amplifies the odd ulp, it does not change the picture
