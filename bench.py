@@ -49,13 +49,20 @@ DEFAULT_WORKLOAD = "cg_p3d512"
 
 # stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL prints its version there) is sent to
 # stderr instead; the JSON goes to a private duplicate of the original stdout.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line: dict):
-    _JSON_OUT.write(json.dumps(line) + "\n")
-    _JSON_OUT.flush()
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def log(*a):
@@ -476,6 +483,7 @@ def load_traffic(workload):
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
