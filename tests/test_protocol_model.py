@@ -1,0 +1,118 @@
+"""Model check (CPU) of the two NVLink protocols used inside the kernels — the mailbox all-reduce
+(csrc/pk_device.cuh: pk_grid_reduce) and the halo push (csrc/pk_spmv.cu: k_halo_push + the HALO kernel) — under random
+interleavings of the ranks' steps.  The model keeps the features the correctness argument rests on: two banks selected
+by sequence parity, payload stores ordered before the flag store, readers that only read after seeing their flags, and
+no other synchronisation between ranks.  Checked: every rank obtains exactly the sum / halo of the right sequence number
+(no stale or overwritten bank is ever read), for thousands of random schedules, including ranks that run far ahead."""
+import random
+
+import pytest
+
+
+def _allreduce_rank(me, P, mbox, n_rounds, values, results):
+    """Generator = one rank's last block; every `yield` is a point where another rank may run."""
+    for seq in range(1, n_rounds + 1):
+        bank = seq & 1
+        v = values[me][seq]
+        for p in range(P):                          # payload stores to every mailbox (own included)
+            mbox[p][bank][me]["payload"] = (seq, v)
+            yield
+        for p in range(P):                          # fence, then flags
+            mbox[p][bank][me]["flag"] = seq
+            yield
+        for p in range(P):                          # wait for the P flags addressed to me
+            while mbox[me][bank][p]["flag"] != seq:
+                yield
+        total = 0
+        for p in range(P):                          # read in rank order
+            s, val = mbox[me][bank][p]["payload"]
+            assert s == seq, f"rank {me} read payload of seq {s} while reducing seq {seq}"
+            total += val
+            yield
+        results[me].append(total)
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+def test_mailbox_allreduce_two_banks_suffice(P):
+    rng = random.Random(P)
+    for trial in range(300):
+        n_rounds = 12
+        values = [[rng.randrange(1000) for _ in range(n_rounds + 1)] for _ in range(P)]
+        mbox = [[[{"payload": (0, 0), "flag": 0} for _ in range(P)] for _ in range(2)] for _ in range(P)]
+        results = [[] for _ in range(P)]
+        gens = [_allreduce_rank(r, P, mbox, n_rounds, values, results) for r in range(P)]
+        alive = list(range(P))
+        # biased scheduler: one rank is strongly favoured so that it runs as far ahead as the protocol allows
+        fav = rng.randrange(P)
+        steps = 0
+        while alive:
+            r = fav if (fav in alive and rng.random() < 0.7) else rng.choice(alive)
+            try:
+                next(gens[r])
+            except StopIteration:
+                alive.remove(r)
+            steps += 1
+            assert steps < 2_000_000, "deadlock in the model"
+        want = [sum(values[p][s] for p in range(P)) for s in range(1, n_rounds + 1)]
+        for r in range(P):
+            assert results[r] == want
+
+
+def _halo_rank(me, P, recv, n_rounds, data, got):
+    """One rank of a ring: push my boundary to both neighbours (side stream), interior work, then the boundary kernel
+    waits for the neighbours' flags of THIS exchange and reads their data; the next push is ordered after that kernel
+    (event) exactly as in spmv_impl()."""
+    nbrs = [q for q in ((me - 1) % P, (me + 1) % P) if q != me]
+    nbrs = sorted(set(nbrs))
+    for seq in range(1, n_rounds + 1):
+        bank = seq & 1
+        for q in nbrs:                              # k_halo_push: data, fence, flag
+            recv[q][bank][me]["data"] = (seq, data[me][seq])
+            yield
+        for q in nbrs:
+            recv[q][bank][me]["flag"] = seq
+            yield
+        for _ in range(3):                          # interior rows
+            yield
+        for q in nbrs:                              # boundary kernel: wait, then read
+            while recv[me][bank][q]["flag"] != seq:
+                yield
+        for q in nbrs:
+            s, val = recv[me][bank][q]["data"]
+            assert s == seq, f"rank {me} read halo of exchange {s} during exchange {seq}"
+            got[me].append((seq, q, val))
+            yield
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_halo_push_two_banks_suffice(P):
+    rng = random.Random(100 + P)
+    for trial in range(300):
+        n_rounds = 10
+        data = [[rng.randrange(1000) for _ in range(n_rounds + 1)] for _ in range(P)]
+        recv = [[[{"data": (0, 0), "flag": 0} for _ in range(P)] for _ in range(2)] for _ in range(P)]
+        got = [[] for _ in range(P)]
+        gens = [_halo_rank(r, P, recv, n_rounds, data, got) for r in range(P)]
+        alive = list(range(P))
+        fav = rng.randrange(P)
+        steps = 0
+        while alive:
+            r = fav if (fav in alive and rng.random() < 0.7) else rng.choice(alive)
+            try:
+                next(gens[r])
+            except StopIteration:
+                alive.remove(r)
+            steps += 1
+            assert steps < 2_000_000, "deadlock in the model"
+        for r in range(P):
+            for seq, q, val in got[r]:
+                assert val == data[q][seq]
+
+
+def test_model_detects_the_single_bank_hazard():
+    """Sanity of the model itself: with ONE bank a fast rank overwrites a payload its peer has not read yet."""
+    src = open(__file__).read().split("def test_model_detects_the_single_bank_hazard")[0].replace("bank = seq & 1", "bank = 0")
+    ns = {}
+    exec(compile(src, "one_bank_model", "exec"), ns)
+    with pytest.raises(AssertionError):
+        ns["test_mailbox_allreduce_two_banks_suffice"](3)
