@@ -70,17 +70,38 @@ def log(*a):
 
 
 def algorithmic_bytes(solver, k, n, nnz):
-    """minimal-traffic model, per solver iteration (and for one operator application)."""
+    """minimal-traffic model, per solver iteration (and for one operator application).
+    MrR: §8d's primary figure B_spmv + 80n (the literal three-phase form moves 104n, see actual_bytes)."""
     b_spmv = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
     if solver == "cg":
         per_it = b_spmv + 72.0 * n
     elif solver == "mrr":
-        per_it = b_spmv + 104.0 * n          # literal form: y read for the phase-1 dots, s-phase re-read, 5R/4W update
+        per_it = b_spmv + 80.0 * n
     elif solver == "kskipcg":
         per_it = ((3 * k + 2) * b_spmv + 8.0 * n * (2 * k + 3) + 56.0 * n * (k + 1)) / (k + 1)
     else:
         per_it = ((3 * k + 2) * b_spmv + 8.0 * n * (2 * k + 3) + 72.0 * n * (k + 1)) / (k + 1)
     return b_spmv, per_it
+
+
+def actual_bytes(solver, k, n, nnz):
+    """Bytes the code REALLY moves per solver iteration with the default kernels (every array pass counted once, x
+    gathers counted as one pass): the k-skip basis reads A once for both chains and the step SpMVs consume A·v in
+    registers, so a trip makes 2k+1 passes over A, not the 3k+2 of §8d's formula."""
+    b_a = 12.0 * nnz + 4.0 * (n + 1)                     # one pass over the CSR arrays
+    if solver == "cg":                                   # SpMV (A, p, v) + xr (4R 2W) + p (2R 1W)
+        return b_a + 16.0 * n + 72.0 * n
+    if solver == "mrr":                                  # SpMV (A, r, Ar, y for the dots) + s-phase (3R) + update (5R 4W)
+        return b_a + 24.0 * n + 24.0 * n + 72.0 * n
+    first = 56.0 if solver == "kskipcg" else 72.0        # un-fused first step of a trip
+    fused = 48.0 if solver == "kskipcg" else 64.0        # step fused into the SpMV epilogue: vectors read + written
+    trip = ((2 * k + 1) * b_a                            # k two-chain basis passes + k fused steps + closing SpMV
+            + k * 32.0 * n                               # two-chain pass: 2 gathers + 2 stores
+            + 8.0 * n * (2 * k + 3)                      # Gram: every basis vector once
+            + first * n + k * fused * n + 16.0 * n)
+    if solver == "adaptivekskipmrr":
+        trip += 16.0 * n                                 # best-x snapshot per trip
+    return trip / (k + 1)
 
 
 def measured_peak_gbs():
@@ -142,17 +163,29 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_solvers():
+    """The CPU implementation the reference arm / cpu_baseline time: the reference's own v3/cpu files staged under
+    oracle/_ref by build() (kind "reference"), else the oracle port (kind "port")."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    fns = ref_loader.load()
+    if fns is not None:
+        return fns, "reference", "oracle/_ref = the reference's own v3/cpu/*.py, unmodified (np.int shim, np.dot proxy for CSR)"
+    import krylov_oracle as oracle
+    return oracle.SOLVERS, "port", "oracle/krylov_oracle.py (port of v3/cpu; oracle/_ref not staged)"
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, timed on this box's host cores.
-    The reference is pure Python (numpy/scipy), so there is no oracle/_ref binary: this runs the oracle PORT
-    (oracle/krylov_oracle.py — bit-identical to /root/reference/v3/cpu on the golden vectors), scipy's serial
-    csr_matvec + OpenBLAS-threaded dots, i.e. all the host threads the reference itself can use."""
+    The reference is pure Python (numpy/scipy): build() stages its v3/cpu files under the git-ignored oracle/_ref and
+    this arm runs THOSE (kind "reference"); without them it runs the oracle port (oracle/krylov_oracle.py —
+    bit-identical to /root/reference/v3/cpu on the golden vectors).  Either way: scipy's serial csr_matvec +
+    OpenBLAS-threaded dots, i.e. all the host threads the reference itself can use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import krylov_oracle as oracle
+    solvers_cpu, cpu_kind, cpu_what = cpu_solvers()
     import host_kernels as hk
     from parallel_krylov_b200 import problems
     solver, k, kind, dims, cap = WORKLOADS[args.workload]
@@ -169,7 +202,7 @@ def run_reference(args):
     probe_it = kk + (1 if solver != "cg" and solver != "kskipcg" else 0)
     kw = {"k": k} if k is not None else {}
     t1 = time.perf_counter()
-    _, info = oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=probe_it, **kw)
+    _, info = solvers_cpu[solver](A, b, tol=1e-8, maxiter=probe_it, **kw)
     per_it = max(info["time"] / max(int(info["nosl"][-1]), 1), 1e-9)
     total_steps = args.steps + args.warmup
     budget_s = 150.0
@@ -177,10 +210,10 @@ def run_reference(args):
     it_per_step = max(kk, (it_per_step // kk) * kk)
     log(f"[reference] probe: {per_it:.3f} s/iteration -> {it_per_step} iterations per step")
     for _ in range(args.warmup):
-        oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
+        solvers_cpu[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
     its, secs = 0, 0.0
     for _ in range(args.steps):
-        _, info = oracle.SOLVERS[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
+        _, info = solvers_cpu[solver](A, b, tol=1e-8, maxiter=it_per_step, **kw)
         its += int(info["nosl"][-1])
         secs += info["time"]
     value = its / secs
@@ -197,8 +230,8 @@ def run_reference(args):
         "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.workload, n, len(val), it_per_step),
-        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": int(blas_threads), "kind": "port",
-                         "sample": sample, "host_cpus": os.cpu_count(),
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": int(blas_threads), "kind": cpu_kind,
+                         "implementation": cpu_what, "sample": sample, "host_cpus": os.cpu_count(),
                          "note": "scipy csr_matvec is serial; numpy dots use OpenBLAS threads"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -240,30 +273,51 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ctx = Context.get(local_rank)
 
+    # ---- parity, where the driver measures: five solvers x two systems through parallel_krylov_b200.mpi.* at THIS GPU
+    # count against the committed outputs of the unmodified reference (tests/golden); see parallel_krylov_b200/selfcheck.py
+    parity = None
+    if not args.no_parity:
+        from parallel_krylov_b200 import selfcheck
+        if world == 1:
+            selfcheck.init_single_rank_group()
+        t_par = time.time()
+        parity = selfcheck.run(None, verbose=bool(os.environ.get("PK_BENCH_VERBOSE")))
+        parity["seconds"] = round(time.time() - t_par, 2)
+        if rank == 0:
+            log(f"[parity] {parity['cases']} cases on {world} GPU(s): ok={parity['ok']} max_dev50={parity['max_dev50']:.2e} "
+                f"(k=4: {parity['max_dev50_k4']:.2e}) in {parity['seconds']}s")
+
     solver, k, kind, dims, cap = WORKLOADS[args.workload]
     if args.maxiter:
         cap = args.maxiter
-    n = int(np.prod(dims)) if kind == "stencil" else dims[0]
-    base = n // world
-    row0 = rank * base
-    n_loc = base if rank < world - 1 else n - row0
+
+    def make_problem(name):
+        """This rank's row block of a workload, generated directly in HBM -> (operator, b, csr tensors, sizes)."""
+        _, _, kind_, dims_, _ = WORKLOADS[name]
+        n_ = int(np.prod(dims_)) if kind_ == "stencil" else dims_[0]
+        base_ = n_ // world
+        row0_ = rank * base_
+        n_loc_ = base_ if rank < world - 1 else n_ - row0_
+        if kind_ == "stencil":
+            rp_, cg_, va_, _ = dp.stencil_csr(*dims_, row0=row0_, n_rows=n_loc_, ctx=ctx)
+        else:
+            rp_, cg_, va_, _ = dp.banded_csr(dims_[0], dims_[1], 0, row0=row0_, n_rows=n_loc_, ctx=ctx)
+        nnz_loc_ = int(va_.numel())
+        b_ = dp.hash_normal(0, n_loc_, offset=row0_, ctx=ctx)
+        if world > 1:
+            from parallel_krylov_b200.mpi import DistOperator
+            offs_ = [r * base_ for r in range(world)] + [n_]
+            op_ = DistOperator.from_local_csr(rp_, cg_, va_, n_, None, ctx, row_offsets=offs_)
+            t_ = torch.tensor([nnz_loc_], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_)
+            nnz_ = int(t_.item())
+        else:
+            op_ = Operator.from_csr_tensors(rp_, cg_, va_, n_, ctx)
+            nnz_ = nnz_loc_
+        return op_, b_, (rp_, cg_, va_), (n_, n_loc_, nnz_, nnz_loc_)
+
     t0 = time.time()
-    if kind == "stencil":
-        rowptr, colg, val, _ = dp.stencil_csr(*dims, row0=row0, n_rows=n_loc, ctx=ctx)
-    else:
-        rowptr, colg, val, _ = dp.banded_csr(dims[0], dims[1], 0, row0=row0, n_rows=n_loc, ctx=ctx)
-    nnz_loc = int(val.numel())
-    b = dp.hash_normal(0, n_loc, offset=row0, ctx=ctx)
-    if world > 1:
-        from parallel_krylov_b200.mpi import DistOperator
-        offs = [r * base for r in range(world)] + [n]
-        op = DistOperator.from_local_csr(rowptr, colg, val, n, None, ctx, row_offsets=offs)
-        t = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        nnz = int(t.item())
-    else:
-        op = Operator.from_csr_tensors(rowptr, colg, val, n, ctx)
-        nnz = nnz_loc
+    op, b, (rowptr, colg, val), (n, n_loc, nnz, nnz_loc) = make_problem(args.workload)
     torch.cuda.synchronize()
     if rank == 0:
         log(f"[ours] {args.workload}: n={n} nnz={nnz} on {world} GPU(s), generated in HBM in {time.time() - t0:.1f}s; "
@@ -377,41 +431,88 @@ def run_ours(args):
         h2d_total, d2h_total = h2d, n_loc * 8
     e2e_value = it2 / (e2e_ms * 1e-3)
 
+    # ---- the other BASELINE.json configs, measured briefly in the same run (default workload only) -------------------
+    # N = 1: configs[1], [2], the north-star's k-skip MrR 256^3 target, CG 256^3, and configs[3], [4] on one GPU;
+    # N > 1: configs[3] (kskipmrr k=8, banded 32M) and configs[4] (adaptivekskipmrr k=8, 512^3) row-partitioned over N.
+    other = None
+    peak, peak_src = measured_peak_gbs()
+    if args.workload == DEFAULT_WORKLOAD and not args.no_other:
+        other = {}
+        torch.cuda.empty_cache()
+        names = (("mrr_p3d128", "kskipcg4_p3d256", "kskipmrr8_p3d256", "cg_p3d256", "mrr_p3d256", "kskipmrr8_band32m",
+                  "adaptive8_p3d512") if world == 1 else ("kskipmrr8_band32m", "adaptive8_p3d512"))
+        for name in names:
+            s2, k2, _, _, cap2 = WORKLOADS[name]
+            op2, b2, csr2, (n2, _, nnz2, _) = make_problem(name)
+            del csr2
+            kw2 = {"k": k2} if k2 is not None else {}
+            solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
+            barrier()
+            e0.record()
+            its2 = 0
+            for _ in range(2):
+                _, i2 = solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
+                its2 += i2["iterations"]
+            e1.record()
+            barrier()
+            ms2 = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t.item())
+            v_its = its2 / (ms2 * 1e-3)
+            _, pib = algorithmic_bytes(s2, k2 or 0, n2, nnz2)
+            act = actual_bytes(s2, k2 or 0, n2, nnz2)
+            other[name] = {"iterations_per_s": v_its, "iterations_per_solve": its2 / 2, "converged": bool(i2["converged"]),
+                           "final_k": i2.get("final_k"),
+                           "frac_formula": pib * v_its / 1e9 / (peak * world),
+                           "frac_actual_bytes": act * v_its / 1e9 / (peak * world),
+                           "bytes_per_iteration_formula": pib, "bytes_per_iteration_actual": act,
+                           "workload": workload_config(name, n2, nnz2, cap2)["workload"]}
+            if rank == 0:
+                log(f"[other] {name}: {v_its:.1f} it/s, frac formula {other[name]['frac_formula']:.3f}, "
+                    f"actual bytes {other[name]['frac_actual_bytes']:.3f}")
+            del op2, b2
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        return 0
+        return 0 if (parity is None or parity["ok"]) else 1
 
     # ---- roofline of the dominant kernel (operator application) -------------------------------------------------
-    peak, peak_src = measured_peak_gbs()
     b_spmv_loc, _ = algorithmic_bytes(solver, k or 0, n_loc, nnz_loc)      # per launch on this rank
     _, per_it_bytes = algorithmic_bytes(solver, k or 0, n, nnz)
+    per_it_actual = actual_bytes(solver, k or 0, n, nnz)
     spmv_avg_ms = prof_ms.value / max(prof_n.value, 1)
     spmv_gbs = b_spmv_loc / (spmv_avg_ms * 1e-3) / 1e9 if spmv_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_spmv_tma (y = A x with fused dots; TMA bulk-copy pipeline)", "achieved": spmv_gbs, "peak": peak,
-                "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": load_traffic(args.workload),
+                "unit": "GB/s", "frac": spmv_gbs / peak,
+                # the ncu capture is of the single-GPU launch; a rank of an N-GPU run moves 1/N of it, so no number is claimed there
+                "traffic": load_traffic(args.workload) if world == 1 else None,
                 "algorithmic_bytes_per_launch": b_spmv_loc, "avg_launch_ms": spmv_avg_ms,
                 "launches_timed": int(prof_n.value), "peak_source": peak_src,
                 "whole_iteration": {"bytes_per_iteration": per_it_bytes,
                                     "achieved_gbs": per_it_bytes * value / 1e9 / 1.0,
-                                    "frac_of_peak_x_gpus": per_it_bytes * value / 1e9 / (peak * world)}}
+                                    "frac_of_peak_x_gpus": per_it_bytes * value / 1e9 / (peak * world),
+                                    "bytes_per_iteration_actual": per_it_actual,
+                                    "frac_actual_bytes": per_it_actual * value / 1e9 / (peak * world)}}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only) -----------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import krylov_oracle as oracle
+        solvers_cpu, cpu_kind, cpu_what = cpu_solvers()
         import scipy.sparse as sp
         A = sp.csr_matrix((h_val.numpy(), h_col.numpy(), h_rowptr.numpy()), shape=(n, n))
         kk = (k or 0) + 1
         m = kk * max(1, int(round(3 / kk))) if nnz > 2e8 else kk * max(1, 20 // kk)
         t_cpu = time.perf_counter()
-        _, ci = oracle.SOLVERS[solver](A, h_b.numpy(), tol=1e-8, maxiter=m, **kw)
+        _, ci = solvers_cpu[solver](A, h_b.numpy(), tol=1e-8, maxiter=m, **kw)
         # extend the sample to ~10-30 s if the first probe was short
         if ci["time"] < 5.0:
             m2 = int(min(cap, m * max(2, int(12.0 / max(ci["time"], 1e-3))))) // kk * kk
-            _, ci = oracle.SOLVERS[solver](A, h_b.numpy(), tol=1e-8, maxiter=max(m2, kk), **kw)
+            _, ci = solvers_cpu[solver](A, h_b.numpy(), tol=1e-8, maxiter=max(m2, kk), **kw)
         try:
             from threadpoolctl import threadpool_info
             blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
@@ -419,39 +520,10 @@ def run_ours(args):
             blas_threads = os.cpu_count()
         cpu_its = int(ci["nosl"][-1])
         cpu_baseline = {"value": cpu_its / ci["time"], "unit": "iterations/s", "cores": int(blas_threads),
-                        "kind": "port", "host_cpus": os.cpu_count(),
-                        "sample": f"{cpu_its} iterations of the same system on the host (oracle/krylov_oracle.py: scipy "
-                                  f"serial csr_matvec + OpenBLAS dots), {ci['time']:.1f}s, timed like the reference"}
+                        "kind": cpu_kind, "implementation": cpu_what, "host_cpus": os.cpu_count(),
+                        "sample": f"{cpu_its} iterations of the same system on the host (scipy serial csr_matvec + "
+                                  f"OpenBLAS dots), {ci['time']:.1f}s, timed like the reference"}
         log(f"[cpu_baseline] {cpu_baseline['value']:.4f} it/s ({time.perf_counter() - t_cpu:.1f}s total)")
-
-    # ---- the other single-GPU BASELINE.json configs, measured briefly in the same run (N=1, default workload only) ---
-    other = None
-    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_other:
-        other = {}
-        del h_rowptr, h_col, h_val, h_b, h_x
-        torch.cuda.empty_cache()
-        for name in ("mrr_p3d128", "kskipcg4_p3d256", "cg_p3d256"):
-            s2, k2, kind2, dims2, cap2 = WORKLOADS[name]
-            rp2, c2, v2, n2 = dp.stencil_csr(*dims2, ctx=ctx)
-            op2 = Operator.from_csr_tensors(rp2, c2, v2, n2, ctx)
-            b2 = dp.hash_normal(0, n2, ctx=ctx)
-            kw2 = {"k": k2} if k2 is not None else {}
-            solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
-            torch.cuda.synchronize()
-            e0.record()
-            its2 = 0
-            for _ in range(2):
-                _, i2 = solve(s2, op2, b2, tol=1e-8, maxiter=cap2, use_graph=True, ctx=ctx, **kw2)
-                its2 += i2["iterations"]
-            e1.record()
-            torch.cuda.synchronize()
-            v_its = its2 / (e0.elapsed_time(e1) * 1e-3)
-            _, pib = algorithmic_bytes(s2, k2 or 0, n2, int(v2.numel()))
-            other[name] = {"iterations_per_s": v_its, "iterations_per_solve": its2 / 2,
-                           "frac_of_hbm_roofline": pib * v_its / 1e9 / peak,
-                           "workload": workload_config(name, n2, int(v2.numel()), cap2)["workload"]}
-            del op2, rp2, c2, v2, b2
-            torch.cuda.empty_cache()
 
     line = {
         "metric": "solver_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
@@ -463,12 +535,15 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_total),
                 "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "exposed_comm": exposed,
-        "other_baseline_configs": other,
+        "other_baseline_configs": other, "parity": parity,
     }
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        log("PARITY FAILED: see the 'parity' object of the JSON line")
+        return 1
     return 0
 
 
@@ -492,6 +567,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--maxiter", type=int, default=0, help="override the per-step iteration cap")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity solves before the timed region")
     ap.add_argument("--no-other", action="store_true", help="skip the brief runs of the other BASELINE configs")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs in the timed region (no per-launch event timing of the SpMV kernel)")

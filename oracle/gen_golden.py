@@ -82,6 +82,9 @@ MATRICES = {
     "band27_20k": ("banded_spd", (20000, 13, 0)),
     "band5_777": ("banded_spd", (777, 2, 3)),
     "dense256": ("dense_spd", (256, 0)),
+    # the two systems bench.py solves through parallel_krylov_b200.mpi.* at every GPU count before its timed region
+    "p3d48": ("poisson3d", (48,)),
+    "band27_100k": ("banded_spd", (100000, 13, 0)),
 }
 
 # solver, k
@@ -112,6 +115,10 @@ CASES.append(("p2d48", "randn", "adaptivekskipmrr", 4, 1e-8, 22))
 CASES.append(("p2d48", "randn", "adaptivekskipmrr", 12, 1e-8, 2000))
 CASES.append(("p2d48", "randn", "adaptivekskipmrr", 16, 1e-8, 2000))
 CASES.append(("p3d16", "randn", "adaptivekskipmrr", 12, 1e-8, 2000))
+# bench.py's driver-visible parity set (N = 1, 2, 4, 8 GPUs): five solvers on two systems
+for mname in ("p3d48", "band27_100k"):
+    for solver, k in (("cg", None), ("mrr", None), ("kskipcg", 2), ("kskipmrr", 4), ("adaptivekskipmrr", 4)):
+        CASES.append((mname, "randn", solver, k, 1e-8, None))
 # loose tolerance: converges at the very first check
 CASES.append(("p3d16", "randn", "cg", None, 10.0, None))
 CASES.append(("p3d16", "randn", "mrr", None, 10.0, None))

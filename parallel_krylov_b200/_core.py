@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import time
 from typing import Optional
 
@@ -17,7 +18,10 @@ import torch
 from . import _lib
 from ._lib import PkError, SolveOpts, SolveResult, check
 
-HIST_CAP = 1 << 22   # history entries kept on the device when maxiter is larger (the reference allocates maxiter+1)
+# History entries kept on the device when maxiter is larger (the reference allocates maxiter+1 doubles + ints up front,
+# /root/reference/v3/cpu/common.py:33-34 — 3 GiB for maxiter = N at 512^3).  Entries beyond the cap are dropped, never
+# written; the solve itself is unaffected, info["history_truncated"] says so, PK_HIST_CAP overrides the cap.
+HIST_CAP = int(os.environ.get("PK_HIST_CAP", 1 << 22))
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -178,7 +182,15 @@ class Operator:
             nonlocal h2d
             if t.device != dev:
                 h2d += t.numel() * torch.empty((), dtype=dtype).element_size()
+            if dtype == torch.int32 and t.dtype != torch.int32 and t.numel():
+                # a wider index type must FIT before it is narrowed: a silent wrap would pass the device-side range check
+                lo, hi = int(t.min()), int(t.max())
+                if lo < 0 or hi >= 2 ** 31:
+                    raise PkError(f"CSR index out of the int32 range ({lo}..{hi}); a block must have nnz < 2^31 and "
+                                  "fewer than 2^31 columns")
             return t.to(device=dev, dtype=dtype).contiguous()
+        if int(n_cols) >= 2 ** 31:
+            raise PkError("a block must have fewer than 2^31 columns (int32 column indices)")
         rowptr, col, val = dv(rowptr, torch.int32), dv(col, torch.int32), dv(val, torch.float64)
         op.tensors = {"rowptr": rowptr, "col": col, "val": val}
         op.n_rows = rowptr.numel() - 1
@@ -417,7 +429,11 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
         "gpu_launches": int(res.kernel_launches),
         "spmv": int(res.spmv_count),
         "h2d_bytes": int(h2d),
+        "history_truncated": bool(res.entries > hist_len),
     }
+    if info["history_truncated"] and ctx.rank == 0:
+        print(f"parallel_krylov_b200: residual history truncated to {hist_len} of {int(res.entries)} entries "
+              "(PK_HIST_CAP raises the cap)", file=sys.stderr)
     if method == "adaptivekskipmrr":
         info["khistory"] = khist[:entries]
         info["final_k"] = int(res.final_k)

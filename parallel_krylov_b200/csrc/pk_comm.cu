@@ -299,10 +299,13 @@ __global__ void k_pack(const int32_t* __restrict__ idx, long long n, const doubl
 
 // Start the halo exchange of x (and x1) on the side stream: the main stream may run interior rows meanwhile.
 int pk_comm_halo_start(pk_ctx* ctx, pk_mat* m, double* x, double* x1) {
-    if (!m->distributed || m->n_halo == 0 || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
-    PK_REQUIRE(ctx->comm != nullptr, "distributed operator without a communicator");
+    if (!m->distributed || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
     const int P = ctx->n_ranks;
     const long long n_send = m->send_off[P];
+    // A rank whose rows are needed by a peer must send even when it references no remote column itself
+    // (structurally nonsymmetric A, e.g. block triangular): the exchange is skipped only if BOTH directions are empty.
+    if (m->n_halo == 0 && n_send == 0) return PK_OK;
+    PK_REQUIRE(ctx->comm != nullptr, "distributed operator without a communicator");
     // x must be complete before it is sent
     PK_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     PK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_a, 0));

@@ -37,6 +37,8 @@ struct PkDots {
 };
 bool pk_mat_can_fuse(const pk_mat* m);
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
+int pk_csr_validate(pk_ctx* ctx, const void* rowptr, int rowptr64, const int32_t* col, long long n_rows,
+                    long long n_cols, long long nnz, int* flags);
 int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result);
 
 // pk_persistent.cu — whole CG loop as one cooperative kernel (small, L2-resident systems)

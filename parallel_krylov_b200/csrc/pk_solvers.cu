@@ -27,10 +27,7 @@ extern "C" const char* pk_last_error(void) { return g_err; }
 extern "C" int pk_version(void) { return PK_VERSION; }
 
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
-    PK_REQUIRE(out != nullptr, "null out");
-    PK_CUDA(cudaSetDevice(device));
-    pk_ctx* c = new pk_ctx();
+static int ctx_init(pk_ctx* c, int device, void* stream) {
     c->device = device;
     c->stream = (cudaStream_t)stream;
     if (c->stream == nullptr) {
@@ -43,7 +40,6 @@ extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
     PK_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
         pk_set_error("libpkrylov is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
-        delete c;
         return PK_ERR_UNSUPPORTED;
     }
     c->sm_count = prop.multiProcessorCount;
@@ -62,6 +58,18 @@ extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
     PK_CUDA(cudaEventCreate(&c->ev_t1));
     PK_CUDA(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
     PK_CUDA(cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming));
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
+    PK_REQUIRE(out != nullptr, "null out");
+    PK_CUDA(cudaSetDevice(device));
+    pk_ctx* c = new pk_ctx();
+    const int rc = ctx_init(c, device, stream);
+    if (rc != PK_OK) {
+        pk_ctx_destroy(c);          // releases whatever the partial initialisation had already acquired
+        return rc;
+    }
     *out = c;
     return PK_OK;
 }
@@ -69,23 +77,20 @@ extern "C" int pk_ctx_create(pk_ctx** out, int device, void* stream) {
 extern "C" int pk_ctx_destroy(pk_ctx* c) {
     if (!c) return PK_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     pk_comm_destroy(c);
-    cudaFree(c->red.partials);
-    cudaFree(c->red.ticket);
-    cudaFree(c->d_state);
+    if (c->red.partials) cudaFree(c->red.partials);
+    if (c->red.ticket) cudaFree(c->red.ticket);
+    if (c->d_state) cudaFree(c->d_state);
     if (c->my_mbox) cudaFree(c->my_mbox);
-    cudaFreeHost(c->h_state);
-    cudaFreeHost(c->h_flags);
-    cudaStreamDestroy(c->side);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    cudaEventDestroy(c->ev_a);
-    cudaEventDestroy(c->ev_b);
-    cudaEventDestroy(c->ev_t0);
-    cudaEventDestroy(c->ev_t1);
-    cudaEventDestroy(c->ev_poll[0]);
-    cudaEventDestroy(c->ev_poll[1]);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_poll[0], c->ev_poll[1]})
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    cudaGetLastError();
     delete c;
     return PK_OK;
 }
@@ -153,6 +158,21 @@ extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_c
     PK_REQUIRE(ctx && out, "null argument");
     PK_REQUIRE(n_rows >= 0 && nnz >= 0 && nnz < (1LL << 31), "CSR block must have 0 <= nnz < 2^31");
     PK_REQUIRE(n_rows == 0 || (d_rowptr && (nnz == 0 || (d_col && d_val))), "null CSR arrays");
+    PK_REQUIRE(n_cols_local >= 0 && n_cols_local < (1LL << 31), "column space of a block must be < 2^31 (int32 indices)");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    {
+        const char* e = getenv("PK_VALIDATE");        // PK_VALIDATE=0 skips the one-time structural check
+        if (n_rows > 0 && !(e && atoi(e) == 0)) {
+            int bad = 0;
+            PK_CHECK(pk_csr_validate(ctx, d_rowptr, 0, d_col, n_rows, n_cols_local, nnz, &bad));
+            if (bad) {
+                pk_set_error("malformed CSR block:%s%s%s%s", (bad & 1) ? " rowptr[0] != 0;" : "",
+                             (bad & 2) ? " rowptr not monotone;" : "", (bad & 4) ? " rowptr[n_rows] != nnz;" : "",
+                             (bad & 8) ? " column index outside [0, n_cols);" : "");
+                return PK_ERR_ARG;
+            }
+        }
+    }
     pk_mat* m = new pk_mat();
     m->ctx = ctx;
     m->n_rows = n_rows;
@@ -371,8 +391,13 @@ struct Solve {
     int run_batches(long long unit, long long already, Body body, long long force_batch = 0) {
         long long batch = force_batch > 0 ? force_batch : o.check_every;
         if (batch <= 0) {
-            // aim for >= ~0.5 ms of device work between polls (rough: 200 bytes per row per iteration at 6 TB/s)
-            double per_it_us = std::max(8.0, (double)n * 200.0 / 6.0e6);
+            // aim for >= ~0.5 ms of device work between polls (rough: 200 bytes per row per iteration at 6 TB/s).
+            // The batch must be the SAME on every rank (each rank enqueues whole batches, and the host-enqueued
+            // collectives of a batch need a matching peer), so it is derived from the global size, never from the
+            // local row count: uneven blocks would otherwise give different batches and hang the NCCL paths.
+            const double rows = (ctx->n_ranks > 1 && o.global_n > 0) ? (double)o.global_n / (double)ctx->n_ranks
+                                                                      : (double)n;
+            double per_it_us = std::max(8.0, rows * 200.0 / 6.0e6);
             batch = (long long)std::ceil(500.0 / (per_it_us * (double)unit));
             batch = std::max<long long>(1, std::min<long long>(batch, 64));
         }
@@ -385,14 +410,18 @@ struct Solve {
             int rc = PK_OK;
             for (long long i = 0; i < batch && rc == PK_OK; ++i) rc = body();
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-            if (rc != PK_OK) return rc;
+            if (rc != PK_OK || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                if (rc != PK_OK) return rc;
+            }
             PK_CUDA(ce);
             graph_launches = ctx->launches - l0;
             graph_spmvs = ctx->spmvs - s0;
             ctx->launches = l0;
             ctx->spmvs = s0;
-            PK_CUDA(cudaGraphInstantiate(&gexec, g, 0));
+            cudaError_t ie = cudaGraphInstantiate(&gexec, g, 0);
             cudaGraphDestroy(g);
+            PK_CUDA(ie);
         }
         long long enq = already;
         int slot = 0, prev = -1;
@@ -639,6 +668,7 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     PK_REQUIRE(opts->maxiter >= 0, "maxiter < 0");
     PK_REQUIRE(hist_len >= 4, "history arrays too short");
     PK_REQUIRE(method != PK_ADAPTIVEKSKIPMRR || d_khistory != nullptr, "adaptivekskipmrr needs d_khistory");
+    PK_REQUIRE(ctx->n_ranks == 1 || opts->global_n > 0, "distributed solve needs opts->global_n");
     PK_CUDA(cudaSetDevice(ctx->device));
     Solve s;
     s.ctx = ctx;

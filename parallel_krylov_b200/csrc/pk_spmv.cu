@@ -910,7 +910,49 @@ __global__ void k_tile_max(const int32_t* __restrict__ rowptr, long long n_rows,
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+// One-time structural check of a CSR block (the scipy-based reference raises on malformed input; silently reading out
+// of bounds is not an option): bit 0 rowptr[0] != 0, bit 1 rowptr not monotone, bit 2 rowptr[n] != nnz,
+// bit 3 a column index outside [0, n_cols).
+template <class RP>
+__global__ void k_csr_validate(const RP* __restrict__ rowptr, const int32_t* __restrict__ col, long long n_rows,
+                               long long n_cols, long long nnz, int* __restrict__ bad) {
+    int f = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 == 0) {
+        if (rowptr[0] != 0) f |= 1;
+        if ((long long)rowptr[n_rows] != nnz) f |= 4;
+    }
+    for (long long r = t0; r < n_rows; r += stride)
+        if (rowptr[r + 1] < rowptr[r]) f |= 2;
+    for (long long q = t0; q < nnz; q += stride) {
+        const int c = col[q];
+        if (c < 0 || (long long)c >= n_cols) f |= 8;
+    }
+    if (f) atomicOr(bad, f);
+}
+
 }  // namespace
+
+int pk_csr_validate(pk_ctx* ctx, const void* rowptr, int rowptr64, const int32_t* col, long long n_rows,
+                    long long n_cols, long long nnz, int* flags) {
+    int* d = nullptr;
+    PK_CUDA(cudaMalloc(&d, sizeof(int)));
+    PK_CUDA(cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+    long long work = nnz > n_rows ? nnz : n_rows;
+    int grid = (int)((work + 1023) / 1024);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    if (rowptr64)
+        k_csr_validate<long long><<<grid, 256, 0, ctx->stream>>>((const long long*)rowptr, col, n_rows, n_cols, nnz, d);
+    else
+        k_csr_validate<int32_t><<<grid, 256, 0, ctx->stream>>>((const int32_t*)rowptr, col, n_rows, n_cols, nnz, d);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(flags, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return PK_OK;
+}
 
 // Largest number of nonzeros in any tile of `tile_rows` consecutive rows (one small pass over rowptr, blocking).
 int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result) {
@@ -1019,7 +1061,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ctx->spmvs += two ? 2 : 1;
 
     if (m->kind == MAT_DENSE) {
-        if (m->distributed && m->n_halo > 0) {
+        if (m->distributed) {
             PK_CHECK(pk_comm_halo_start(ctx, m, x, x1));
             PK_CHECK(pk_comm_halo_wait(ctx));
         }
@@ -1053,7 +1095,8 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.reduce = (dots.w || (dots.fuse && dots.epi != EPI_KS_STEP)) ? 1 : 0;
     int grid = 0;
 
-    if (!m->distributed || m->n_halo == 0) {
+    const bool exchange = m->distributed && (m->n_halo > 0 || (!m->send_off.empty() && m->send_off.back() > 0));
+    if (!exchange) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
     } else if (m->halo_p2p && m->use_tma && !ctx->nocomm) {
