@@ -72,6 +72,10 @@ struct pk_ctx {
     double* my_mbox = nullptr;
     std::vector<void*> peer_mbox;    // opened IPC mappings (to close)
     int n_ranks = 1, rank = 0;
+    // predicates the launch helpers copy into PkRedArgs (set by the adaptive solver around its device-conditional launches)
+    int ctl_only_rollback = 0;
+    int ctl_dyn_cj = -1;
+    int ctl_dyn_last = 0;
     bool nocomm = false;             // measurement aid: same kernels, no halo exchange / all-reduce (numerically meaningless)
     long long launches = 0;          // kernels launched (statistics)
     long long spmvs = 0;

@@ -66,7 +66,22 @@ struct PkRedArgs {
     // multi-GPU all-reduce fused into this kernel's last block (NVLink peer stores into per-rank mailboxes)
     const PkP2P* p2p;       // nullptr: single GPU, or NCCL path (defer = 1)
     int ar_n;               // doubles to all-reduce once the local sums are published (0: local publish only)
+    // Launch sequences whose shape depends on device-resident state (adaptivekskipmrr: the guard and the current k live
+    // in PkState, so the host enqueues the sequence for the initial k and kernels decide for themselves):
+    int only_rollback;      // 1: the kernel runs only when st->rollback != 0 (the rollback branch of a trip)
+    int dyn_cj;             // >= 0: index of a k-skip step / basis level (or 0 for the Gram kernel): skipped when > st->k
+    int dyn_last;           // 1 (step kernels): the reduction + epilogue happen only when dyn_cj == st->k (last step of the trip)
 };
+
+// Should this kernel do nothing?  (stop flag raised, or a predicated launch whose condition is false.)  Uniform across
+// the grid — and across ranks, because the state it reads was computed from all-reduced, bit-identical sums.
+__device__ __forceinline__ bool pk_skip(const PkRedArgs& ra) {
+    const volatile PkState* st = ra.st;
+    if (st->done != 0) return true;
+    if (ra.only_rollback && st->rollback == 0) return true;
+    if (ra.dyn_cj >= 0 && ra.dyn_cj > st->k) return true;
+    return false;
+}
 
 // --------------------------------------------------------------------------------------------------------------
 // Rounding discipline: the library is compiled with -fmad=false so that a*b+c rounds twice exactly like numpy's

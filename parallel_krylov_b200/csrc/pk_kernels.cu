@@ -19,7 +19,7 @@ __device__ __forceinline__ bool pk_done(const PkState* st) { return *((volatile 
 // ---- dot ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_BLOCK) k_dot(long long n, const double* __restrict__ u,
                                                   const double* __restrict__ v, PkRedArgs ra, int ignore_done) {
-    if (!ignore_done && pk_done(ra.st)) return;
+    if (!ignore_done && pk_skip(ra)) return;
     double acc[1] = {0.0};
     const long long stride = (long long)gridDim.x * EW_BLOCK;
     for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) acc[0] += u[i] * v[i];
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_dot(long long n, const double* __r
 __global__ void __launch_bounds__(EW_BLOCK) k_resid_init(long long n, const double* __restrict__ b,
                                                          const double* __restrict__ v, double* __restrict__ r,
                                                          double* __restrict__ p, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     double acc[1] = {0.0};
     const long long stride = (long long)gridDim.x * EW_BLOCK;
     for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_resid_init(long long n, const doub
 __global__ void __launch_bounds__(EW_BLOCK) k_cg_xr(long long n, double* __restrict__ x, double* __restrict__ r,
                                                     const double* __restrict__ p, const double* __restrict__ v,
                                                     PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     const double alpha = ra.st->alpha;
     double acc[1] = {0.0};
     const long long stride = (long long)gridDim.x * EW_BLOCK;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_cg_p(long long n, double* __restri
 __global__ void __launch_bounds__(EW_BLOCK) k_mrr_first(long long n, const double* __restrict__ ar,
                                                         double* __restrict__ r, double* __restrict__ x,
                                                         double* __restrict__ y, double* __restrict__ z, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     const double zeta = ra.st->zeta;
     const double nzeta = -zeta;
     double acc[1] = {0.0};
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_first(long long n, const doubl
 __global__ void __launch_bounds__(EW_BLOCK) k_mrr_s(long long n, const double* __restrict__ ar,
                                                     const double* __restrict__ y, const double* __restrict__ r,
                                                     PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     const double gamma = ra.st->gamma;
     double acc[2] = {0.0, 0.0};
     const long long stride = (long long)gridDim.x * EW_BLOCK;
@@ -110,9 +110,17 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_s(long long n, const double* _
 //      v3/cpu/mrr.py:45-48 ; kskipmrr.py:65-69 / :89-93 with (zeta, eta) = coef[2j], coef[2j+1]
 __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const double* __restrict__ ar,
                                                          double* __restrict__ y, double* __restrict__ z,
-                                                         const double* r, double* r_out, double* __restrict__ x, int cj,
-                                                         PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+                                                         const double* r, double* r_out, double* r_alt,
+                                                         double* __restrict__ x, int cj, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    bool reduce = ra.epi != EPI_KS_STEP;
+    if (ra.dyn_cj >= 0) {
+        // k lives on the device (adaptive): this is the last step of the trip iff cj == k; the residual ping-pongs
+        // between its home (r_out) and the spare buffer (r_alt) so that the LAST step of the trip ends at home
+        const int kk = ra.st->k;
+        if (ra.dyn_last) reduce = (cj == kk);
+        if (r_alt != nullptr && ((kk - cj) & 1)) r_out = r_alt;
+    }
     const double zeta = (cj < 0) ? ra.st->zeta : ra.st->coef[2 * cj];
     const double eta = (cj < 0) ? ra.st->eta : ra.st->coef[2 * cj + 1];
     double acc[1] = {0.0};
@@ -128,14 +136,25 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const doub
         x[i] = x[i] - zi;
         acc[0] += ri * ri;
     }
-    if (ra.epi != EPI_KS_STEP) pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+    if (reduce) pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+// ---- adaptive: at the top of a trip either remember x (pre_x = x.copy(), adaptivekskipmrr.py:69) or roll x back to it
+//      (x = pre_x.copy(), :48), as the guard decided (st->rollback)
+__global__ void __launch_bounds__(EW_BLOCK) k_adapt_save(long long n, double* __restrict__ x, double* __restrict__ best_x,
+                                                         const PkState* st) {
+    if (pk_done(st)) return;
+    const bool back = *((volatile const int*)&st->rollback) != 0;
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    if (back) for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) x[i] = best_x[i];
+    else for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) best_x[i] = x[i];
 }
 
 // ---- k-skip CG step: x += a Ap0 ; Ar0 -= a Ap1 ; Ap0 = Ar0 + b Ap0 ; sums[0] = Ar0.Ar0  — kskipcg.py:53-55 -----
 __global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* __restrict__ x,
                                                           double* __restrict__ ar0, const double* ap0, double* ap0_out,
                                                           const double* __restrict__ ap1, int cj, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     const double alpha = ra.st->coef[2 * cj];
     const double beta = ra.st->coef[2 * cj + 1];
     double acc[1] = {0.0};
@@ -157,7 +176,8 @@ __global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* _
 template <int W, int MODE>
 __global__ void __launch_bounds__(EW_BLOCK) k_gram(long long n, long long ld, const double* __restrict__ U, int nu,
                                                    const double* __restrict__ V, int nv, int j0, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
+    if (ra.dyn_cj >= 0) { nu = ra.st->k + 2; nv = ra.st->k + 1; }      // adaptive (MrR layout): rows of the CURRENT k only
     double acc[6 * W];
 #pragma unroll
     for (int t = 0; t < 6 * W; ++t) acc[t] = 0.0;
@@ -189,7 +209,8 @@ __global__ void __launch_bounds__(EW_BLOCK) k_gram(long long n, long long ld, co
 template <int W, int MODE, int STAGES>
 __global__ void __launch_bounds__(EW_BLOCK) k_gram_tma(long long n, long long ld, const double* __restrict__ U, int nu,
                                                        const double* __restrict__ V, int nv, int j0, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
+    if (ra.dyn_cj >= 0) { nu = ra.st->k + 2; nv = ra.st->k + 1; }      // adaptive (MrR layout): rows of the CURRENT k only
     constexpr int T = EW_BLOCK;                     // elements per tile (one per thread)
     constexpr int ROWS = 2 * (W + 1);
     extern __shared__ __align__(128) unsigned char gsm_raw[];
@@ -272,8 +293,10 @@ __global__ void __launch_bounds__(EW_BLOCK) k_gram_tma(long long n, long long ld
     pk_grid_reduce<6 * W, EW_BLOCK, true>(acc, ra);
 }
 
-__global__ void k_scalar(PkState* st, int epi, int ignore_done) {
+__global__ void k_scalar(PkState* st, int epi, int ignore_done, int only_rollback, int dyn_cj, int dyn_last) {
     if (!ignore_done && pk_done(st)) return;
+    if (only_rollback && st->rollback == 0) return;
+    if (dyn_cj >= 0 && (dyn_cj > st->k || (dyn_last && dyn_cj != st->k))) return;
     pk_epilogue<true>(epi, st);
 }
 
@@ -306,6 +329,9 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
     ra.store_only = 0;
     ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
     ra.ar_n = 0;          // set by the launcher: number of sums this kernel all-reduces
+    ra.only_rollback = ctx->ctl_only_rollback;
+    ra.dyn_cj = ctx->ctl_dyn_cj;
+    ra.dyn_last = ctx->ctl_dyn_last;
     return ra;
 }
 
@@ -358,7 +384,8 @@ int pk_blocks_per_sm(const void* kernel, int block, size_t smem) {
 }
 
 int pk_launch_scalar(pk_ctx* ctx, int epi, int ignore_done) {
-    k_scalar<<<1, 1, 0, ctx->stream>>>(ctx->d_state, epi, ignore_done);
+    k_scalar<<<1, 1, 0, ctx->stream>>>(ctx->d_state, epi, ignore_done, ctx->ctl_only_rollback, ctx->ctl_dyn_cj,
+                                       ctx->ctl_dyn_last);
     PK_LAUNCH_CHECK();
     return PK_OK;
 }
@@ -416,9 +443,15 @@ int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y,
     return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
 }
 
+int pk_launch_adapt_save(pk_ctx* ctx, long long n, double* x, double* best_x) {
+    k_adapt_save<<<ew_grid(ctx, k_adapt_save, n), EW_BLOCK, 0, ctx->stream>>>(n, x, best_x, ctx->d_state);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
 int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, const double* r,
-                         double* r_out, double* x, int cj, int epi) {
-    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, r_out, x, cj, red_args_n(ctx, epi, 1));
+                         double* r_out, double* r_alt, double* x, int cj, int epi) {
+    k_mrr_update<<<ew_grid(ctx, k_mrr_update, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, z, r, r_out, r_alt, x, cj, red_args_n(ctx, epi, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, epi, -1, 0);
 }

@@ -18,7 +18,8 @@ int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, d
                         int epi);
 int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r);
 int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, const double* r,
-                         double* r_out, double* x, int cj, int epi);
+                         double* r_out, double* r_alt, double* x, int cj, int epi);
+int pk_launch_adapt_save(pk_ctx* ctx, long long n, double* x, double* best_x);
 int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, const double* ap0, double* ap0_out,
                           const double* ap1, int cj, int epi);
 int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const double* U, int nu, const double* V, int nv,

@@ -522,7 +522,7 @@ struct Solve {
         PK_CHECK(run_batches(1, 1, [&]() -> int {
             PK_CHECK(apply(r, ar, y, EPI_MRR_GAMMA));             // Ar ; nu = y.Ar ; mu = y.y ; gamma
             PK_CHECK(pk_launch_mrr_s(ctx, n, ar, y, r));          // s = Ar - gamma y ; zeta, eta
-            PK_CHECK(pk_launch_mrr_update(ctx, n, ar, y, z, r, r, x, -1, EPI_MRR_STEP));
+            PK_CHECK(pk_launch_mrr_update(ctx, n, ar, y, z, r, r, nullptr, x, -1, EPI_MRR_STEP));
             return PK_OK;
         }));
         return PK_OK;
@@ -569,29 +569,76 @@ struct Solve {
     }
 
     // ---- k-skip MrR: /root/reference/v3/cpu/kskipmrr.py:8-108 ------------------------------------------------
-    int kskipmrr_open(double* Ar0, double* Ar1, double* Ay0, double* z) {
+    int kskipmrr_open(double* Ar0, double* Ar1, double* Ay0, double* z, int first_epi) {
         PK_CHECK(apply(Ar0, Ar1, Ar0, EPI_MRR_FIRST));            // kskipmrr.py:26-27
-        PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, EPI_KS_FIRST));   // :28-34
+        PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, first_epi));      // :28-34
         return apply(Ar0, Ar1);                                   // invariant: Ar[1] = A Ar[0] at trip start
     }
-    int kskipmrr_trip(int k, int k_alloc) {
+    // Launch-time predicates copied into every kernel launched inside the scope (pk_device.cuh: pk_skip).
+    struct Ctl {
+        pk_ctx* c;
+        Ctl(pk_ctx* c_, int only_rollback, int dyn_cj, int dyn_last) : c(c_) {
+            c->ctl_only_rollback = only_rollback;
+            c->ctl_dyn_cj = dyn_cj;
+            c->ctl_dyn_last = dyn_last;
+        }
+        ~Ctl() {
+            c->ctl_only_rollback = 0;
+            c->ctl_dyn_cj = -1;
+            c->ctl_dyn_last = 0;
+        }
+    };
+
+    // One outer trip.  dyn = false: k is known to the host (kskipmrr).  dyn = true (adaptivekskipmrr): the sequence is
+    // enqueued for k = k_alloc, the CURRENT k lives in PkState: levels / steps beyond it are skipped by the kernels
+    // themselves, the step with cj == k reduces r.r and runs the trip-end epilogue, and the Ar0 ping-pong picks its
+    // side from the parity of the device k.
+    int kskipmrr_trip(int k, int k_alloc, bool dyn = false) {
         auto Ar = [&](int j) { return vec(j); };                  // rows 0..k_alloc+1
         auto Ay = [&](int j) { return vec(k_alloc + 2 + j); };    // rows 0..k_alloc
         double* z = vec(2 * k_alloc + 3);
         double* spare = vec(2 * k_alloc + 4);                     // second home of Ar[0] for the fused steps
-        for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
-        PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
-        if (!pk_mat_can_fuse(A)) {
+        const int end_epi = dyn ? EPI_ADAPT_TRIP_END : EPI_KS_TRIP_END;
+        for (int j = 1; j <= k; ++j) {
+            Ctl c(ctx, 0, dyn ? j : -1, 0);
+            PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
+        }
+        {
+            Ctl c(ctx, 0, dyn ? 0 : -1, 0);
+            PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
+        }
+        // The dynamic ping-pong needs the kernel to choose the vector it multiplies, which a host-side halo exchange
+        // cannot follow: distributed adaptive solves keep update and SpMV separate.
+        const bool fuse = pk_mat_can_fuse(A) && !(dyn && A->distributed);
+        if (!fuse) {
             for (int j = 0; j <= k; ++j) {
-                PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), Ar(0), x, j,
-                                              j == k ? EPI_KS_TRIP_END : EPI_KS_STEP));
+                {
+                    Ctl c(ctx, 0, dyn ? j : -1, dyn ? 1 : 0);
+                    PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), Ar(0), nullptr, x, j,
+                                                  (dyn || j == k) ? end_epi : EPI_KS_STEP));
+                }
+                Ctl c(ctx, 0, dyn ? j : -1, 0);
                 PK_CHECK(apply(Ar(0), Ar(1)));
             }
             return PK_OK;
         }
+        if (dyn) {
+            {
+                Ctl c(ctx, 0, 0, 1);
+                PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), Ar(0), spare, x, 0, end_epi));
+            }
+            for (int j = 1; j <= k; ++j) {
+                Ctl c(ctx, 0, j, 1);
+                PkDots d;
+                d.epi = end_epi;
+                d.fuse = 1; d.cj = j; d.f_a = Ay(0); d.f_b = z; d.f_x = x; d.f_out = spare;   // (home, spare): kernel picks
+                PK_CHECK(pk_launch_spmv(ctx, A, Ar(0), nullptr, nullptr, nullptr, d));
+            }
+            return apply(Ar(0), Ar(1));
+        }
         // Fused steps (see kskipcg): Ar1 = A Ar0 lives only in registers; Ar0 ping-pongs between home and `spare`.
         double* cur = (k % 2 == 1) ? spare : Ar(0);
-        PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), cur, x, 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
+        PK_CHECK(pk_launch_mrr_update(ctx, n, Ar(1), Ay(0), z, Ar(0), cur, nullptr, x, 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
         for (int j = 1; j <= k; ++j) {
             double* nxt = (cur == spare) ? Ar(0) : spare;
             PkDots d;
@@ -607,53 +654,37 @@ struct Solve {
         double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k + 2), *z = vec(2 * k + 3);
         PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
-        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z));
+        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z, EPI_KS_FIRST));
         PK_CHECK(run_batches(k + 1, 1, [&]() -> int { return kskipmrr_trip(k, k); }));
         return PK_OK;
     }
 
     // ---- adaptive k-skip MrR: /root/reference/v3/cpu/adaptivekskipmrr.py:8-141 (normative variant) -----------
-    // The residual-growth guard changes k, i.e. the launch sequence, so the host looks at the residual once per
-    // trip (one small D2H per k+1 iterations).
-    int adaptive(int* final_k, int* host_converged) {
+    // The residual-growth guard (:45-69) runs ON THE DEVICE: a one-thread kernel at the top of each trip decides
+    // rollback / convergence / stop from the residual the previous trip recorded (EPI_ADAPT_GUARD), the rollback branch
+    // is a fixed sequence of kernels predicated on that decision, and the trip itself is enqueued for the initial k
+    // with the current k read from PkState by the kernels.  No host synchronisation per trip: the host polls the stop
+    // flag once per batch like the other solvers, and the whole batch is graph-capturable.
+    int adaptive() {
         const int k0 = o.k;
-        int k = k0;
         double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k0 + 2), *z = vec(2 * k0 + 3), *best_x = vec(2 * k0 + 5);
-        PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
+        PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));                  // :23-25 (pre_residual = residual[0])
+        PK_CUDA(cudaMemcpyAsync(best_x, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
-        PK_CHECK(fetch_state());
-        double best_res = std::sqrt(ctx->h_state->rr) / ctx->h_state->bnorm;   // adaptivekskipmrr.py:24
-        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z));
-        *host_converged = 0;
-        while (true) {
-            PK_CHECK(fetch_state());
-            const PkState* h = ctx->h_state;
-            if (h->done && !h->converged) break;                  // `while i < maxiter` failed
-            if (h->it >= o.maxiter) break;
-            double res = std::sqrt(h->rr) / h->bnorm;
-            if (res > best_res) {                                 // :45 residual grew: roll back, one plain MrR step
-                if (h->done) PK_CUDA(cudaMemsetAsync(&ctx->d_state->done, 0, 2 * sizeof(int), ctx->stream));
-                PK_CUDA(cudaMemcpyAsync(x, best_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-                PK_CHECK(apply(x, Ar1));                          // :48  Ar[0] = b - A x
+        PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z, EPI_ADAPT_FIRST));               // :28-40
+        PK_CHECK(run_batches(k0 + 1, 1, [&]() -> int {
+            PK_CHECK(pk_launch_scalar(ctx, EPI_ADAPT_GUARD, 0));                  // :43-47, :67-68, :72-74
+            PK_CHECK(pk_launch_adapt_save(ctx, n, x, best_x));                    // :48 x = pre_x  |  :69 pre_x = x
+            {
+                Ctl c(ctx, 1, -1, 0);                                             // the rollback branch, :49-66
+                PK_CHECK(apply(x, Ar1));
                 PK_CHECK(pk_launch_resid_init(ctx, n, b, Ar1, Ar0, nullptr, EPI_NONE));
-                PK_CHECK(apply(Ar0, Ar1, Ar0, EPI_MRR_FIRST));    // :49-52
-                PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, EPI_ADAPT_STEP));   // :53-61
+                PK_CHECK(apply(Ar0, Ar1, Ar0, EPI_MRR_FIRST));
+                PK_CHECK(pk_launch_mrr_first(ctx, n, Ar1, Ar0, x, Ay0, z, EPI_ADAPT_STEP));
                 PK_CHECK(apply(Ar0, Ar1));
-                if (k > 1) k -= 1;                                // :64-65
-                PK_CHECK(pk_launch_set_k(ctx, k));                // st->k = k ; khist[idx] = k (:66)
-                PK_CHECK(fetch_state());
-                res = std::sqrt(ctx->h_state->rr) / ctx->h_state->bnorm;
-            } else {
-                best_res = res;                                   // :68-69
-                PK_CUDA(cudaMemcpyAsync(best_x, x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
             }
-            if (res < o.tol) {                                    // :72
-                *host_converged = 1;
-                break;
-            }
-            PK_CHECK(kskipmrr_trip(k, k0));
-        }
-        *final_k = k;
+            return kskipmrr_trip(k0, k0, true);                                   // :77-128 with the device's k
+        }));
         return PK_OK;
     }
 };
@@ -683,14 +714,14 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     ctx->launches = 0;
     ctx->spmvs = 0;
     PK_CHECK(s.init_state(d_residual, d_nosl, method == PK_ADAPTIVEKSKIPMRR ? d_khistory : nullptr, hist_len));
-    int final_k = opts->k, host_conv = -1;
+    int final_k = opts->k;
     int rc = PK_OK;
     switch (method) {
         case PK_CG: rc = s.cg(); break;
         case PK_MRR: rc = s.mrr(); break;
         case PK_KSKIPCG: rc = s.kskipcg(); break;
         case PK_KSKIPMRR: rc = s.kskipmrr(); break;
-        case PK_ADAPTIVEKSKIPMRR: rc = s.adaptive(&final_k, &host_conv); break;
+        case PK_ADAPTIVEKSKIPMRR: rc = s.adaptive(); break;
         default: pk_set_error("unknown method %d", method); return PK_ERR_ARG;
     }
     if (rc != PK_OK) {
@@ -709,8 +740,8 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     }
     result->iterations = h->it;
     result->entries = h->idx + 1;
-    result->converged = host_conv >= 0 ? host_conv : h->converged;
-    result->final_k = final_k;
+    result->converged = h->converged;
+    result->final_k = (method == PK_ADAPTIVEKSKIPMRR) ? h->k : final_k;
     result->final_residual = std::sqrt(h->rr) / h->bnorm;
     result->elapsed_s = (double)ms * 1e-3;
     result->kernel_launches = ctx->launches;

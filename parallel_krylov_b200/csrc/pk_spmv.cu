@@ -58,7 +58,7 @@ struct SpmvArgs {
 
 template <int NV, int BLOCK, bool VEC>
 __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sval = reinterpret_cast<double*>(smem_raw);              // [cap]
     int* scol = reinterpret_cast<int*>(sval + a.cap);                // [cap]
@@ -187,7 +187,7 @@ struct TileMeta {
 
 template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
 __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[STAGES];
     __shared__ TileMeta meta[STAGES];
@@ -201,6 +201,18 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     double acc[3] = {0.0, 0.0, 0.0};
     const double c0 = FUSE ? ra.st->coef[2 * a.cj] : 0.0;       // zeta | alpha
     const double c1 = FUSE ? ra.st->coef[2 * a.cj + 1] : 0.0;   // eta  | beta
+    if (FUSE && ra.dyn_cj >= 0) {
+        // k lives on the device (adaptive): the host passed x0 = home and f_out = spare of the ping-pong pair; step cj
+        // reads the home buffer iff (k - cj + 1) is even, so that the last step of the trip (cj == k) writes home, and
+        // only that last step reduces r.r and runs the trip-end epilogue
+        const int kk = ra.st->k;
+        if ((kk - a.cj + 1) & 1) {
+            const double* t = a.x0;
+            a.x0 = a.f_out;
+            a.f_out = const_cast<double*>(t);
+        }
+        if (ra.dyn_last) a.reduce = (a.cj == kk) ? 1 : 0;
+    }
     // tile index space: tiles of [row_lo,row_hi) followed by tiles of [row_lo2,row_hi2)
     const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
     const long long tiles_b = a.row_hi2 > a.row_lo2 ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
@@ -466,7 +478,7 @@ struct PatArgs {
 
 template <int NV, int FUSE>
 __global__ void __launch_bounds__(256) k_spmv_pat(PatArgs pa, SpmvArgs a, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     extern __shared__ __align__(16) unsigned char psm[];
     double* tval = reinterpret_cast<double*>(psm);                 // [n_ent]
     int* toff = reinterpret_cast<int*>(tval + pa.n_ent);           // [n_ent]
@@ -477,6 +489,15 @@ __global__ void __launch_bounds__(256) k_spmv_pat(PatArgs pa, SpmvArgs a, PkRedA
     double acc[3] = {0.0, 0.0, 0.0};
     const double c0 = FUSE ? ra.st->coef[2 * a.cj] : 0.0;
     const double c1 = FUSE ? ra.st->coef[2 * a.cj + 1] : 0.0;
+    if (FUSE && ra.dyn_cj >= 0) {          // see k_spmv_tma: device-resident k picks the side of the ping-pong pair
+        const int kk = ra.st->k;
+        if ((kk - a.cj + 1) & 1) {
+            const double* t = a.x0;
+            a.x0 = a.f_out;
+            a.f_out = const_cast<double*>(t);
+        }
+        if (ra.dyn_last) a.reduce = (a.cj == kk) ? 1 : 0;
+    }
     const long long na = a.row_hi > a.row_lo ? a.row_hi - a.row_lo : 0;
     const long long nb = a.row_hi2 > a.row_lo2 ? a.row_hi2 - a.row_lo2 : 0;
     // R rows per thread are in flight together (ids, epilogue operands and gathers of all R rows are independent):
@@ -602,8 +623,11 @@ __global__ void k_pattern_verify(const int32_t* __restrict__ rowptr, const int32
 // Owner-side halo push: store the entries each peer needs straight into that peer's receive buffer over NVLink, fence,
 // then (last block) raise the sequence flags.  Replaces pack kernel + ncclSend/ncclRecv + the side stream.
 __global__ void __launch_bounds__(256) k_halo_push(PkHaloPush hp, const double* __restrict__ x0,
-                                                   const double* __restrict__ x1, const PkState* st) {
+                                                   const double* __restrict__ x1, const PkState* st, int only_rollback,
+                                                   int dyn_cj) {
     if (pk_done(st)) return;
+    if (only_rollback && *((volatile const int*)&st->rollback) == 0) return;
+    if (dyn_cj >= 0 && dyn_cj > *((volatile const int*)&st->k)) return;
     const unsigned long long seq = *hp.seq + 1ull;
     const int bank = (int)(seq & 1ull);
     const long long total = hp.send_off[hp.n_ranks];
@@ -672,7 +696,7 @@ struct GemvArgs {
 
 template <int NV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_gemv(GemvArgs a, PkRedArgs ra) {
-    if (pk_done(ra.st)) return;
+    if (pk_skip(ra)) return;
     constexpr int NW = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[3] = {0.0, 0.0, 0.0};
@@ -1058,6 +1082,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
+    ra.only_rollback = ctx->ctl_only_rollback;
+    ra.dyn_cj = ctx->ctl_dyn_cj;
+    ra.dyn_last = ctx->ctl_dyn_last;
     ctx->spmvs += two ? 2 : 1;
 
     if (m->kind == MAT_DENSE) {
@@ -1112,7 +1139,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
             if (pg < 1) pg = 1;
             PK_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
             PK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_a, 0));
-            k_halo_push<<<pg, 256, 0, ctx->side>>>(m->push, x, x1, ctx->d_state);
+            k_halo_push<<<pg, 256, 0, ctx->side>>>(m->push, x, x1, ctx->d_state, ctx->ctl_only_rollback, ctx->ctl_dyn_cj);
             PK_CUDA(cudaGetLastError());
             PK_CUDA(cudaEventRecord(ctx->ev_b, ctx->side));
             ctx->launches++;

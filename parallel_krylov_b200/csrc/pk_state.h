@@ -20,8 +20,8 @@ struct PkState {
     // control
     int done;             // 1: every later kernel of the stream is a no-op (stopping rule already fired)
     int converged;        // isConverged
-    int guard;            // adaptive: residual grew (host handles the rollback)
-    int pad0;
+    int guard;            // < 0: an in-kernel wait for a peer timed out (-1 all-reduce, -2 halo)
+    int rollback;         // adaptive: the residual grew — this trip starts with the rollback branch (set by EPI_ADAPT_GUARD)
     long long it;         // `i` of the reference loops (number of solution updates)
     long long idx;        // `index` (history position); == it for cg/mrr
     long long maxiter;
@@ -30,6 +30,7 @@ struct PkState {
     // cg / mrr scalars
     double gamma, alpha, beta, zeta, eta, mu, nu;
     double rr;            // ||r||^2 of the newest residual
+    double best_res;      // adaptive: `pre_residual`, the smallest residual seen at a trip start
     // k-skip: coefficient pairs of the k+1 steps of one trip: (alpha_j, beta_j) or (zeta_j, eta_j)
     double coef[2 * (PK_KMAX + 1)];
     double gram[PK_GRAM_MAX];
@@ -62,7 +63,10 @@ enum PkEpi : int {
     EPI_GRAM_CG,         // gram[] complete         -> coef[] = (alpha_j, beta_j)
     EPI_GRAM_MRR,        // gram[] complete         -> coef[] = (zeta_j, eta_j)
     EPI_GRAM_PART,       // a Gram window that is not the last: copy sums into gram[] only
-    EPI_ADAPT_STEP,      // adaptive rollback step: it++, idx++, res[idx]  (no stop test; host lowers k)
+    EPI_ADAPT_STEP,      // adaptive rollback step: it++, idx++, res[idx], k = max(k-1, 1), khist[idx], convergence test
+    EPI_ADAPT_FIRST,     // adaptive opening step: it = idx = 1 recorded (the loop-top logic is EPI_ADAPT_GUARD)
+    EPI_ADAPT_TRIP_END,  // red[0] = r.r            -> it += k+1, idx++, res[idx], khist[idx]  (tested by the next guard)
+    EPI_ADAPT_GUARD,     // (no sums) loop condition, residual-growth guard, convergence test at the top of a trip
 };
 
 
@@ -129,7 +133,9 @@ PK_HD inline void pk_epilogue(int epi, PkState* st) {
             st->rr = s[0];
             st->it = 0;
             st->idx = 0;
-            pk_record(st, 0, 0, sqrt(s[0]) / st->bnorm, true);
+            st->best_res = sqrt(s[0]) / st->bnorm;          // adaptivekskipmrr.py:24  pre_residual = residual[0]
+            st->rollback = 0;
+            pk_record(st, 0, 0, st->best_res, true);
             break;
         }
         case EPI_MRR_FIRST:               // v3/cpu/mrr.py:19   zeta = (r.Ar)/(Ar.Ar)
@@ -163,11 +169,51 @@ PK_HD inline void pk_epilogue(int epi, PkState* st) {
             pk_stop_test(st, res);
             break;
         }
-        case EPI_ADAPT_STEP: {            // v3/cpu/adaptivekskipmrr.py:58-61 (rollback step; host lowers k)
+        case EPI_ADAPT_STEP: {            // v3/cpu/adaptivekskipmrr.py:58-66 (end of the rollback branch), then :72-74
             st->rr = s[0];
             st->it += 1;
             st->idx += 1;
-            pk_record(st, st->idx, st->it, sqrt(s[0]) / st->bnorm, false);
+            double res = sqrt(s[0]) / st->bnorm;
+            pk_record(st, st->idx, st->it, res, false);
+            if (st->k > 1) st->k -= 1;                      // :64-65
+            if (st->khist && st->idx < st->hist_len) st->khist[st->idx] = st->k;   // :66
+            if (res < st->tol) {                            // :72 (no `i < maxiter` test here: that is the loop top)
+                st->converged = 1;
+                st->done = 1;
+            }
+            break;
+        }
+        case EPI_ADAPT_FIRST: {           // v3/cpu/adaptivekskipmrr.py:36-40  i = index = 1
+            st->rr = s[0];
+            st->it += 1;
+            st->idx = st->it;
+            pk_record(st, st->idx, st->it, sqrt(s[0]) / st->bnorm, true);
+            break;
+        }
+        case EPI_ADAPT_TRIP_END: {        // v3/cpu/adaptivekskipmrr.py:125-128; residual[index] of :44 recorded here
+            st->rr = s[0];
+            st->it += st->k + 1;
+            st->idx += 1;
+            pk_record(st, st->idx, st->it, sqrt(s[0]) / st->bnorm, true);
+            break;
+        }
+        case EPI_ADAPT_GUARD: {           // v3/cpu/adaptivekskipmrr.py:43-47 and :67-74 — the top of a trip, on the device
+            st->rollback = 0;
+            if (!(st->it < st->maxiter)) {                  // `while i < maxiter` failed: not converged (:129-131)
+                st->converged = 0;
+                st->done = 1;
+                break;
+            }
+            double res = sqrt(st->rr) / st->bnorm;
+            if (res > st->best_res) {                       // :46 the residual grew: this trip opens with the rollback
+                st->rollback = 1;
+            } else {
+                st->best_res = res;                         // :68 (pre_x is saved by k_adapt_save)
+                if (res < st->tol) {                        // :72
+                    st->converged = 1;
+                    st->done = 1;
+                }
+            }
             break;
         }
         case EPI_GRAM_CG:

@@ -46,6 +46,8 @@ double hs_get(void* p, int what, int j) {
         case 7: return (double)st->it;
         case 8: return (double)st->idx;
         case 9: return st->coef[j];
+        case 10: return (double)st->rollback;
+        case 11: return (double)st->k;
         default: return 0.0;
     }
 }

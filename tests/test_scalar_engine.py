@@ -250,56 +250,43 @@ def test_device_scalar_engine_drives_whole_solves_bitwise(host_lib, solver, k, c
 
 
 def _emulate_adaptive(lib, A, b, tol, maxiter, k0):
-    """Solve::adaptive() of csrc/pk_solvers.cu restated: the device engine keeps the history, the host reads one
-    residual per trip, applies the residual-growth guard, rolls back and lowers k."""
+    """Solve::adaptive() of csrc/pk_solvers.cu restated with numpy standing in for the vector kernels.  The guard, the
+    rollback decision, the lowering of k and every stopping decision are taken by the DEVICE engine (EPI_ADAPT_GUARD /
+    EPI_ADAPT_STEP / EPI_ADAPT_TRIP_END of pk_state.h); this driver only does what the predicated kernels do."""
     n = b.size
     x = np.zeros(n)
     e = Engine(lib, maxiter, tol, k0, with_khist=True)
-    lib.hs_set_k.argtypes = [C.c_void_p, C.c_int]
-    k = k0
+    ROLLBACK, K = 10, 11
     Ar = np.zeros((k0 + 2, n)); Ay = np.zeros((k0 + 1, n))
     e.epi("EPI_BNORM", np.dot(b, b))
-    bnorm = np.sqrt(np.dot(b, b))
     Ar[0] = b - A.dot(x)
-    rr = np.dot(Ar[0], Ar[0])
-    e.epi("EPI_RES0", rr)
-    best_res = np.sqrt(rr) / bnorm
-    best_x = None
+    e.epi("EPI_RES0", np.dot(Ar[0], Ar[0]))
+    best_x = x.copy()
 
     def opening(epi_name):
-        nonlocal x, z, rr
+        nonlocal x, z
         Ar[1] = A.dot(Ar[0])
         e.epi("EPI_MRR_FIRST", np.dot(Ar[0], Ar[1]), np.dot(Ar[1], Ar[1]), np.dot(Ar[0], Ar[0]))
         ze = e.get(ZETA)
         Ay[0] = ze * Ar[1]; z = (-ze) * Ar[0]; Ar[0] = Ar[0] - Ay[0]; x = x - z
-        rr = np.dot(Ar[0], Ar[0])
-        e.epi(epi_name, rr)
+        e.epi(epi_name, np.dot(Ar[0], Ar[0]))
         Ar[1] = A.dot(Ar[0])
 
     z = None
-    opening("EPI_KS_FIRST")
-    converged = False
+    opening("EPI_ADAPT_FIRST")
     while True:
-        if e.get(DONE) and not e.get(CONV):
+        e.epi("EPI_ADAPT_GUARD")                       # k_scalar at the top of every trip
+        if e.get(DONE):
             break
-        if e.get(IT) >= maxiter:
-            break
-        res = np.sqrt(rr) / bnorm
-        if res > best_res:
+        if e.get(ROLLBACK):                            # k_adapt_save + the only_rollback kernels
             x = best_x.copy()
             Ar[0] = b - A.dot(x)
             opening("EPI_ADAPT_STEP")
-            if k > 1:
-                k -= 1
-            lib.hs_set_k(e.st, k)
-            e.khist[int(e.get(IDX))] = k
-            res = np.sqrt(rr) / bnorm
+            if e.get(DONE):
+                break
         else:
-            best_res = res
             best_x = x.copy()
-        if res < tol:
-            converged = True
-            break
+        k = int(e.get(K))                              # kernels read the current k from the device state
         for j in range(1, k + 1):
             Ar[j + 1] = A.dot(Ar[j]); Ay[j] = A.dot(Ay[j - 1])
         e.gram("EPI_GRAM_MRR", _gram_layout(0, Ar[: k + 2], Ay[: k + 1], k))
@@ -310,12 +297,11 @@ def _emulate_adaptive(lib, A, b, tol, maxiter, k0):
             Ar[0] = Ar[0] - Ay[0]
             x = x - z
             if j == k:
-                rr = np.dot(Ar[0], Ar[0])
-                e.epi("EPI_KS_TRIP_END", rr)
+                e.epi("EPI_ADAPT_TRIP_END", np.dot(Ar[0], Ar[0]))
             Ar[1] = A.dot(Ar[0])
     m = int(e.get(IDX)) + 1
     out = {"residual": e.res[:m].copy(), "nosl": e.nosl[:m].copy(), "khistory": e.khist[:m].copy(),
-           "converged": converged}
+           "converged": bool(e.get(CONV))}
     lib.hs_free(e.st)
     return x, out
 
@@ -358,3 +344,18 @@ def test_product_and_pow_squares_differ_by_at_most_one_ulp(host_lib, host_lib_po
         host_lib_pow.host_kskipmrr_coef(G.ctypes.data, k, c2.ctypes.data)
         worst = max(worst, float(np.max(np.abs(c1 - c2) / np.abs(c2))))
     assert worst < 1e-9        # the recurrence amplifies the odd ulp, it does not change the picture
+
+
+@pytest.mark.parametrize("cap", [1, 2, 7, 22])
+def test_adaptive_guard_iteration_caps_bitwise(host_lib, cap):
+    """`while i < maxiter` is evaluated by the device guard at the top of every trip: tiny and mid-trip caps end exactly
+    where the reference ends (k-skip trips may overshoot the cap by up to k)."""
+    A = problems.to_scipy(*problems.poisson2d(24))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    xo, io = oracle.adaptivekskipmrr(A, b.copy(), tol=1e-8, maxiter=cap, k=4)
+    x, info = _emulate_adaptive(host_lib, A, b, 1e-8, cap, 4)
+    assert np.array_equal(info["nosl"], io["nosl"])
+    assert np.array_equal(info["residual"], io["residual"])
+    assert np.array_equal(info["khistory"], io["khistory"])
+    assert np.array_equal(x, xo)
+    assert info["converged"] is False
