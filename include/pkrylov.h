@@ -91,13 +91,16 @@ int pk_mat_set_patterns(pk_mat* mat, int n_pat, int n_entries, const uint16_t* d
 int pk_mat_set_halo(pk_mat* mat, int n_peers_total, const int64_t* send_off, const int64_t* recv_off,
                     const int32_t* d_send_idx, const int32_t* h_send_idx, int64_t interior_lo, int64_t interior_hi);
 
-/* Optional NVLink push path for the halo (no NCCL, no side stream): each rank exports its halo receive buffer
- * (pk_mat_halo_p2p_handle), the handles are all-gathered, and pk_mat_halo_p2p_open maps the peers' buffers;
- * dst_off[q] = where this rank's entries start inside q's halo (q's recv_off[this rank]), peer_nhalo[q] = q's halo
- * length.  pk_spmv then pushes boundary entries with plain stores + a sequence flag and the boundary rows wait on the
- * flags inside the SpMV kernel. */
+/* Halo exchange fused into the operator kernel over NVLink peer memory (the default when the peers' buffers can be
+ * mapped; no NCCL, no side stream, one launch): each rank exports its halo receive buffer (pk_mat_halo_p2p_handle), the
+ * handles are all-gathered, and pk_mat_halo_p2p_open maps the peers' buffers; dst_off[q] = where this rank's entries
+ * start inside q's halo (q's recv_off[this rank]), peer_nhalo[q] = q's halo length.  The SpMV kernel then pushes this
+ * rank's boundary entries with plain remote stores + a sequence flag at its start, runs the interior tiles while the
+ * peers' entries are in flight and waits for the peers' flags right before its boundary tiles.
+ * pk_mat_halo_p2p_disable returns the block to the ncclSend/ncclRecv exchange (all ranks must agree on the path). */
 int pk_mat_halo_p2p_handle(pk_mat* mat, char handle[PK_IPC_HANDLE_BYTES]);
 int pk_mat_halo_p2p_open(pk_mat* mat, const char* handles, const int64_t* dst_off, const int64_t* peer_nhalo);
+int pk_mat_halo_p2p_disable(pk_mat* mat);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* communicator (NCCL over NVLink).  Replaces MultiGpu.joint_mpi(comm) (v3/gpu/mpi/common.py:168-171).

@@ -51,6 +51,7 @@ _SIGS = {
     "pk_mat_set_halo": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _I64, _I64]),
     "pk_mat_halo_p2p_handle": (C.c_int, [_P, C.c_char_p]),
     "pk_mat_halo_p2p_open": (C.c_int, [_P, C.c_char_p, _P, _P]),
+    "pk_mat_halo_p2p_disable": (C.c_int, [_P]),
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "pk_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "pk_comm_destroy": (C.c_int, [_P]),

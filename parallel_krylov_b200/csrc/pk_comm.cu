@@ -192,10 +192,11 @@ extern "C" int pk_mat_halo_p2p_open(pk_mat* m, const char* handles, const int64_
         hp.peer_nhalo[q] = peer_nhalo[q];
         hp.send_first[q] = m->send_first[q];
         hp.send_contig[q] = m->send_contig[q];
-        if (m->recv_off[q + 1] > m->recv_off[q]) hp.recv_mask |= (1u << q);
         if (q == me) { hp.peer_recv[q] = m->d_recvbuf; continue; }
-        const bool needed = m->send_off[q + 1] > m->send_off[q];
-        if (!needed) continue;                      // nothing to push to q: no mapping needed
+        // q is a peer if entries flow in EITHER direction (symmetric by construction: my send to q is q's receive from me)
+        const bool needed = m->send_off[q + 1] > m->send_off[q] || m->recv_off[q + 1] > m->recv_off[q];
+        if (!needed) continue;                      // no exchange with q: no mapping, no flags
+        hp.peer_mask |= (1u << q);
         cudaIpcMemHandle_t ih;
         memcpy(&ih, handles + (size_t)q * PK_IPC_HANDLE_BYTES, PK_IPC_HANDLE_BYTES);
         void* ptr = nullptr;
@@ -212,11 +213,18 @@ extern "C" int pk_mat_halo_p2p_open(pk_mat* m, const char* handles, const int64_
     PK_CUDA(cudaMemset(hp.seq, 0, sizeof(unsigned long long)));
     PK_CUDA(cudaMalloc(&hp.ticket, sizeof(unsigned int)));
     PK_CUDA(cudaMemset(hp.ticket, 0, sizeof(unsigned int)));
-    PK_CUDA(cudaMalloc(&hp.recv_seq, sizeof(unsigned long long)));
-    PK_CUDA(cudaMemset(hp.recv_seq, 0, sizeof(unsigned long long)));
-    PK_CUDA(cudaMalloc(&hp.recv_ticket, sizeof(unsigned int)));
-    PK_CUDA(cudaMemset(hp.recv_ticket, 0, sizeof(unsigned int)));
+    PK_CUDA(cudaMalloc(&hp.ticket_done, sizeof(unsigned int)));
+    PK_CUDA(cudaMemset(hp.ticket_done, 0, sizeof(unsigned int)));
+    PK_CUDA(cudaMalloc(&m->d_push, sizeof(PkHaloPush)));
+    PK_CUDA(cudaMemcpy(m->d_push, &hp, sizeof(PkHaloPush), cudaMemcpyHostToDevice));
     m->halo_p2p = true;
+    return PK_OK;
+}
+
+extern "C" int pk_mat_halo_p2p_disable(pk_mat* m) {
+    PK_REQUIRE(m != nullptr, "null operator");
+    PK_CUDA(cudaSetDevice(m->ctx->device));
+    pk_mat_halo_p2p_close(m);
     return PK_OK;
 }
 
@@ -225,10 +233,10 @@ void pk_mat_halo_p2p_close(pk_mat* m) {
     m->peer_recv_maps.clear();
     if (m->push.seq) cudaFree(m->push.seq);
     if (m->push.ticket) cudaFree(m->push.ticket);
-    if (m->push.recv_seq) cudaFree(m->push.recv_seq);
-    if (m->push.recv_ticket) cudaFree(m->push.recv_ticket);
-    m->push.recv_seq = nullptr;
-    m->push.recv_ticket = nullptr;
+    if (m->push.ticket_done) cudaFree(m->push.ticket_done);
+    m->push.ticket_done = nullptr;
+    if (m->d_push) cudaFree(m->d_push);
+    m->d_push = nullptr;
     if (m->d_recvbuf) cudaFree(m->d_recvbuf);
     m->d_recvbuf = nullptr;
     m->push.seq = nullptr;

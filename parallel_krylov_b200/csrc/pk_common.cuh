@@ -88,10 +88,12 @@ struct pk_ctx {
     std::vector<std::pair<cudaEvent_t, int>> seg_ev;
 };
 
-// Halo exchange by direct NVLink stores (no NCCL on the data path): the owner of x pushes the entries its peers need
-// straight into their receive buffers (peer-mapped through CUDA IPC) and raises a sequence flag; the peer's boundary-row
-// SpMV waits on the flags.  Receive buffer of a rank: [32 doubles of flags: flag[bank][source]] then
-// data[bank 0..1][vector 0..1][n_halo].
+// Halo exchange by direct NVLink stores, fused into the operator kernel (no NCCL on the data path): at its start the
+// SpMV kernel of the owner pushes the entries its peers need straight into their receive buffers (peer-mapped through
+// CUDA IPC) and raises a sequence flag; the peer's boundary tiles, scheduled last in its own SpMV kernel, wait on the
+// flags.  Receive buffer of a rank: [32 doubles of flags: flag[bank][source]] then data[bank 0..1][vector 0..1][n_halo].
+// Flags go BOTH ways between any two ranks that exchange in at least one direction (peer_mask is symmetric), so a rank
+// can never run two exchanges ahead of a peer: two banks suffice even for one-directional (nonsymmetric) patterns.
 constexpr int PK_HALO_HDR = 32;
 struct PkHaloPush {
     double* peer_recv[PK_MAX_RANKS];     // peer q's receive buffer as mapped on this device (own buffer at [me])
@@ -101,12 +103,11 @@ struct PkHaloPush {
     int send_first[PK_MAX_RANKS];
     int send_contig[PK_MAX_RANKS];
     const int32_t* send_idx;
-    unsigned long long* seq;             // exchanges pushed (device counter, advanced by the push kernel)
-    unsigned int* ticket;
-    unsigned long long* recv_seq;        // exchanges consumed (advanced by the boundary-row kernel; same value on all ranks)
-    unsigned int* recv_ticket;
+    unsigned long long* seq;             // exchanges completed (advanced by the last block to leave the SpMV kernel)
+    unsigned int* ticket;                // blocks that have finished their share of the push
+    unsigned int* ticket_done;           // blocks that have left the kernel
     int n_ranks, me;
-    unsigned int recv_mask;              // bit p set: peer p sends to me
+    unsigned int peer_mask;              // bit p set: rank p and I exchange entries in at least one direction
 };
 
 enum PkMatKind : int { MAT_CSR_STREAM = 0, MAT_CSR_VECTOR = 1, MAT_DENSE = 2 };
@@ -137,6 +138,7 @@ struct pk_mat {
     // NVLink push path (replaces ncclSend/Recv when the peers' receive buffers are mapped)
     bool halo_p2p = false;
     PkHaloPush push{};
+    PkHaloPush* d_push = nullptr;                // owned: device copy of `push` (the SpMV kernel reads it)
     double* d_recvbuf = nullptr;                 // owned: [PK_HALO_HDR + 4 * n_halo]
     std::vector<void*> peer_recv_maps;           // IPC mappings to close
     long long interior_lo = 0, interior_hi = 0;

@@ -51,6 +51,31 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
         : "memory");
 }
 
+// ---- waiting for a peer's flag (NVLink mailboxes, halo push) ------------------------------------------------------------
+// Poll a flag in this GPU's own memory until it holds `want`.  The first polls are back to back (the common case: the
+// peer is a few microseconds behind); after that the thread backs off with nanosleep so that a long wait does not
+// hammer L2, and the wall-clock budget (PK_SPIN_TIMEOUT_NS of %globaltimer, not a poll count) bounds a wait for a peer
+// that died: the caller then stops the solve with an error instead of hanging the GPU.
+constexpr unsigned long long PK_SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long pk_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool pk_spin_until(const volatile unsigned long long* flag, unsigned long long want) {
+    if (*flag == want) return true;
+    unsigned int polls = 0, ns = 32;
+    unsigned long long t0 = 0;
+    while (*flag != want) {
+        if (++polls < 256) continue;
+        if (t0 == 0) t0 = pk_globaltimer();
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+        if ((polls & 63u) == 0 && pk_globaltimer() - t0 > PK_SPIN_TIMEOUT_NS) return false;
+    }
+    return true;
+}
+
 struct PkRedArgs {
     double* partials;       // [nsums][max_blocks]
     unsigned int* ticket;
@@ -164,14 +189,10 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
             *f = seq;
             volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(
                 pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + threadIdx.x)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
-            long long spins = 0;
-            while (*mine != seq) {
-                if (++spins > (1ll << 31)) {          // a peer never arrived: stop the solve instead of hanging
-                    ra.st->done = 1;
-                    ra.st->converged = 0;
-                    ra.st->guard = -1;
-                    break;
-                }
+            if (!pk_spin_until(mine, seq)) {          // a peer never arrived: stop the solve instead of hanging
+                ra.st->done = 1;
+                ra.st->converged = 0;
+                ra.st->guard = -1;
             }
         }
         __threadfence_system();

@@ -607,9 +607,11 @@ struct Solve {
             Ctl c(ctx, 0, dyn ? 0 : -1, 0);
             PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
         }
-        // The dynamic ping-pong needs the kernel to choose the vector it multiplies, which a host-side halo exchange
-        // cannot follow: distributed adaptive solves keep update and SpMV separate.
-        const bool fuse = pk_mat_can_fuse(A) && !(dyn && A->distributed);
+        // The dynamic ping-pong needs the kernel to choose the vector it multiplies, which a host-enqueued halo exchange
+        // (ncclSend/Recv of a host-known pointer) cannot follow: only the exchange fused into the SpMV kernel can, so
+        // distributed adaptive solves on the NCCL halo path keep update and SpMV separate.
+        const bool inkernel_halo = A->halo_p2p && A->use_tma && !A->pat_on;
+        const bool fuse = pk_mat_can_fuse(A) && !(dyn && A->distributed && !inkernel_halo);
         if (!fuse) {
             for (int j = 0; j <= k; ++j) {
                 {

@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "pk_device.cuh"
 #include "pk_launch.h"
 
@@ -32,14 +34,15 @@ struct SpmvArgs {
     double* y1;
     const double* w;        // fused dots against this vector (nullable)
     long long row_lo, row_hi;
-    long long row_lo2, row_hi2;   // optional second row range processed by the same launch (boundary rows above/below)
-    // halo received by NVLink push: columns >= n_own read from the receive buffer after waiting for the peers' flags
-    const double* hrecv;          // receive buffer base (nullptr: columns index x directly)
-    unsigned long long* hseq;     // exchanges consumed so far (this kernel waits for hseq+1 and advances it)
-    unsigned int* hticket;
+    long long row_lo2, row_hi2;   // optional second and third row ranges processed by the same launch, after the first:
+    long long row_lo3, row_hi3;   // the boundary rows above / below the interior
+    // Halo exchange fused into this kernel (HALO variant): every block first pushes its share of the boundary entries of
+    // x into the peers' receive buffers over NVLink, the tiles of the first range (interior rows: no halo column) run
+    // while the peers' pushes are in flight, and a block waits for the peers' flags right before its first boundary tile
+    // (ranges 2 and 3), whose halo columns (>= n_own) are then read from this rank's receive buffer.
+    const double* hrecv;          // this rank's receive buffer (nullptr: no exchange, columns index x directly)
+    const PkHaloPush* hp;         // push descriptor in device memory
     long long n_own, n_halo;
-    unsigned int recv_mask;
-    int n_ranks;
     long long nnz_total;
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
     int cap;                // staging capacity (nonzeros) per right-hand side
@@ -185,8 +188,14 @@ struct TileMeta {
     int pad;
 };
 
+// Resident blocks per SM the fused-exchange variants are compiled for: the same as their plain counterparts reach (4 for
+// the single-vector SpMV with 256-row tiles, 3 for the two-chain and fused-step forms), so that a rank of a multi-GPU
+// run streams A with as many bulk copies in flight as a single GPU does.
+template <int NV, int BLOCK, bool HALO, int FUSE>
+constexpr int spmv_min_blocks() { return (HALO && BLOCK == 256) ? ((NV == 1 && FUSE == 0) ? 4 : 3) : 1; }
+
 template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
-__global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
+__global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>()) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     if (pk_skip(ra)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[STAGES];
@@ -213,13 +222,15 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         }
         if (ra.dyn_last) a.reduce = (a.cj == kk) ? 1 : 0;
     }
-    // tile index space: tiles of [row_lo,row_hi) followed by tiles of [row_lo2,row_hi2)
+    // tile index space: tiles of [row_lo,row_hi), then of [row_lo2,row_hi2), then of [row_lo3,row_hi3)
     const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
     const long long tiles_b = a.row_hi2 > a.row_lo2 ? (a.row_hi2 - a.row_lo2 + BLOCK - 1) / BLOCK : 0;
-    const long long n_tiles = tiles_a + tiles_b;
+    const long long tiles_c = a.row_hi3 > a.row_lo3 ? (a.row_hi3 - a.row_lo3 + BLOCK - 1) / BLOCK : 0;
+    const long long n_tiles = tiles_a + tiles_b + tiles_c;
     auto tile_rows = [&](long long tile, long long& r0, long long& rend) {
         if (tile < tiles_a) { r0 = a.row_lo + tile * BLOCK; rend = a.row_hi; }
-        else { r0 = a.row_lo2 + (tile - tiles_a) * BLOCK; rend = a.row_hi2; }
+        else if (tile < tiles_a + tiles_b) { r0 = a.row_lo2 + (tile - tiles_a) * BLOCK; rend = a.row_hi2; }
+        else { r0 = a.row_lo3 + (tile - tiles_a - tiles_b) * BLOCK; rend = a.row_hi3; }
     };
     // Tile -> block assignment.  strided (default): tile = b + i*grid, i.e. the grid is one moving window over A.
     // blocked (PK_TILE_ORDER=blocked): block b owns the contiguous tiles [b*chunk, (b+1)*chunk), which turns the
@@ -291,27 +302,58 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         if (STAGES - 1 < my_tiles) endpoints(STAGES - 1, nb, ne);
     }
 
-    // Halo pushed by the peers over NVLink: wait (once per block) for the flags of this exchange; the bulk copies of
-    // the first tiles are already in flight.  Halo entries are then read from the receive buffer, bypassing L1.
-    const double* h0 = nullptr;
-    const double* h1 = nullptr;
-    unsigned long long hseq_next = 0;
-    if (HALO) {
-        const unsigned long long seq = *a.hseq + 1ull;
-        hseq_next = seq;
-        const int bank = (int)(seq & 1ull);
-        if (tid < a.n_ranks && ((a.recv_mask >> tid) & 1u)) {
+    // ---- halo exchange, part 1: push.  The bulk copies of the first tiles are already in flight.  Sequence number of
+    // this exchange = completed exchanges + 1 (the counter is advanced by the last block to LEAVE the kernel, so every
+    // block reads the same value); its parity selects the bank of the peers' receive buffers.
+    bool halo_ready = true;            // false until this block has seen the peers' flags of this exchange
+    __shared__ int push_last;
+    // (the sequence number and the receive-buffer pointers are recomputed where they are needed instead of being kept
+    // in registers across the tile loop: the interior tiles must not pay for the exchange)
+    auto wait_halo = [&]() {           // all threads of the block
+        const unsigned long long hseq = *a.hp->seq + 1ull;
+        if (tid < a.hp->n_ranks && ((a.hp->peer_mask >> tid) & 1u)) {
             const volatile unsigned long long* f =
-                reinterpret_cast<const volatile unsigned long long*>(a.hrecv) + bank * PK_MAX_RANKS + tid;
-            long long spins = 0;
-            while (*f != seq) {
-                if (++spins > (1ll << 31)) { ra.st->done = 1; ra.st->converged = 0; ra.st->guard = -2; break; }
-            }
+                reinterpret_cast<const volatile unsigned long long*>(a.hrecv) + (int)(hseq & 1ull) * PK_MAX_RANKS + tid;
+            if (!pk_spin_until(f, hseq)) { ra.st->done = 1; ra.st->converged = 0; ra.st->guard = -2; }
         }
         __threadfence_system();
         __syncthreads();
-        h0 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 0) * a.n_halo - a.n_own;   // indexed by the column itself
-        h1 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 1) * a.n_halo - a.n_own;
+        halo_ready = true;
+    };
+    if (HALO) {
+        const PkHaloPush* hp = a.hp;
+        const unsigned long long hseq = *hp->seq + 1ull;
+        const int bank = (int)(hseq & 1ull);
+        const int P = hp->n_ranks;
+        const long long total = hp->send_off[P];
+        const long long stride = (long long)gridDim.x * BLOCK;
+        for (long long i = (long long)blockIdx.x * BLOCK + tid; i < total; i += stride) {
+            int q = 0;
+            while (i >= hp->send_off[q + 1]) ++q;
+            const long long kq = i - hp->send_off[q];
+            const long long src = hp->send_contig[q] ? (long long)hp->send_first[q] + kq : (long long)hp->send_idx[i];
+            const long long nh = hp->peer_nhalo[q];
+            double* dst = hp->peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh + hp->dst_off[q] + kq;
+            dst[0] = a.x0[src];
+            if (NV == 2) dst[nh] = a.x1[src];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();      // cumulative: orders the whole block's remote stores (bar.sync above) before the ticket
+            push_last = (atomicAdd(hp->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (push_last) {
+            // every block's entries are on their way: raise this exchange's flag at every peer I talk to (also the ones
+            // that only send to me — the flag is their licence to reuse this bank two exchanges from now)
+            __threadfence_system();
+            if (tid < P && ((hp->peer_mask >> tid) & 1u)) {
+                volatile unsigned long long* f =
+                    reinterpret_cast<volatile unsigned long long*>(hp->peer_recv[tid]) + bank * PK_MAX_RANKS + hp->me;
+                *f = hseq;
+            }
+        }
+        halo_ready = false;
     }
     const int n_own = (int)a.n_own;
 
@@ -340,6 +382,86 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
             a.f_a[row] = rn;
             a.f_out[row] = rn + c1 * xr;
             acc[0] += rn * rn;
+        }
+    };
+
+    // Row phase of one tile.  BND (boundary tile of the fused exchange): columns >= n_own are halo entries and are read
+    // from the receive buffer with L2 loads (they were written by a peer during this kernel); everything else gathers x
+    // through the read-only path.
+    auto row_phase = [&](auto bnd_tag, bool staged, int nr, long long r0, const int* rp, int rofs, int q0,
+                         const int* scol, const double* sval) {
+        constexpr bool BND = decltype(bnd_tag)::value;
+        const double* h0 = nullptr;    // halo entries of the two vectors in the receive buffer, indexed by the column itself
+        const double* h1 = nullptr;
+        if (BND) {
+            const int bank = (int)((*a.hp->seq + 1ull) & 1ull);
+            h0 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 0) * a.n_halo - a.n_own;
+            h1 = a.hrecv + PK_HALO_HDR + (size_t)(bank * 2 + 1) * a.n_halo - a.n_own;
+        }
+        if (staged) {
+            if (tid < nr) {
+                const int sb = rp[rofs + tid] - q0, se = rp[rofs + tid + 1] - q0;
+                const long long row = r0 + tid;
+                // operands of the epilogue are requested before the row loop: their latency is hidden behind it
+                const double wi = (FUSE == 0 && a.w) ? __ldg(a.w + row) : 0.0;
+                const double fa = FUSE ? a.f_a[row] : 0.0;
+                const double fb = (FUSE == 1) ? a.f_b[row] : 0.0;
+                const double fx = FUSE ? a.f_x[row] : 0.0;
+                const double xr = FUSE ? __ldg(a.x0 + row) : 0.0;
+                double sum0 = 0.0, sum1 = 0.0;
+                constexpr int UNR = 8;
+                for (int j = sb; j < se; j += UNR) {
+                    double vv[UNR], xa[UNR], xb[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const bool ok = j + u < se;
+                        const int c = ok ? scol[j + u] : 0;
+                        vv[u] = ok ? sval[j + u] : 0.0;
+                        if (!BND) {
+                            xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
+                            if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
+                        } else {
+                            const bool own = c < n_own;
+                            xa[u] = ok ? (own ? __ldg(a.x0 + c) : __ldcg(h0 + c)) : 0.0;
+                            if (NV == 2) xb[u] = ok ? (own ? __ldg(a.x1 + c) : __ldcg(h1 + c)) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        if (j + u < se) {
+                            sum0 += vv[u] * xa[u];
+                            if (NV == 2) sum1 += vv[u] * xb[u];
+                        }
+                    }
+                }
+                finish_row(row, sum0, sum1, wi, fa, fb, fx, xr);
+            }
+        } else {
+            for (int r = warp; r < nr; r += NW) {
+                const int sb = rp[r], se = rp[r + 1];
+                double sum0 = 0.0, sum1 = 0.0;
+                for (int q = sb + lane; q < se; q += 32) {
+                    const int c = a.col[q];
+                    const double v = a.val[q];
+                    if (!BND || c < n_own) {
+                        sum0 += v * __ldg(a.x0 + c);
+                        if (NV == 2) sum1 += v * __ldg(a.x1 + c);
+                    } else {
+                        sum0 += v * __ldcg(h0 + c);
+                        if (NV == 2) sum1 += v * __ldcg(h1 + c);
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    sum0 += __shfl_down_sync(0xffffffffu, sum0, off);
+                    if (NV == 2) sum1 += __shfl_down_sync(0xffffffffu, sum1, off);
+                }
+                if (lane == 0) {
+                    const long long row = r0 + r;
+                    finish_row(row, sum0, sum1, (FUSE == 0 && a.w) ? a.w[row] : 0.0, FUSE ? a.f_a[row] : 0.0,
+                               (FUSE == 1) ? a.f_b[row] : 0.0, FUSE ? a.f_x[row] : 0.0, FUSE ? a.x0[row] : 0.0);
+                }
+            }
         }
     };
 
@@ -379,84 +501,31 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
             }
             __syncthreads();
         }
-        if (staged) {
-            if (tid < nr) {
-                const int sb = rp[rofs + tid] - q0, se = rp[rofs + tid + 1] - q0;
-                const long long row = r0 + tid;
-                // operands of the epilogue are requested before the row loop: their latency is hidden behind it
-                const double wi = (FUSE == 0 && a.w) ? __ldg(a.w + row) : 0.0;
-                const double fa = FUSE ? a.f_a[row] : 0.0;
-                const double fb = (FUSE == 1) ? a.f_b[row] : 0.0;
-                const double fx = FUSE ? a.f_x[row] : 0.0;
-                const double xr = FUSE ? __ldg(a.x0 + row) : 0.0;
-                double sum0 = 0.0, sum1 = 0.0;
-                constexpr int UNR = 8;
-                for (int j = sb; j < se; j += UNR) {
-                    double vv[UNR], xa[UNR], xb[UNR];
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        const bool ok = j + u < se;
-                        const int c = ok ? scol[j + u] : 0;
-                        vv[u] = ok ? sval[j + u] : 0.0;
-                        if (!HALO) {
-                            xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
-                            if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
-                        } else {   // boundary rows: halo columns live in the receive buffer (branch-free select, L2 loads)
-                            const double* s0 = c < n_own ? a.x0 : h0;
-                            xa[u] = ok ? __ldcg(s0 + c) : 0.0;
-                            if (NV == 2) {
-                                const double* s1 = c < n_own ? a.x1 : h1;
-                                xb[u] = ok ? __ldcg(s1 + c) : 0.0;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        if (j + u < se) {
-                            sum0 += vv[u] * xa[u];
-                            if (NV == 2) sum1 += vv[u] * xb[u];
-                        }
-                    }
-                }
-                finish_row(row, sum0, sum1, wi, fa, fb, fx, xr);
-            }
-        } else {
-            for (int r = warp; r < nr; r += NW) {
-                const int sb = rp[r], se = rp[r + 1];
-                double sum0 = 0.0, sum1 = 0.0;
-                for (int q = sb + lane; q < se; q += 32) {
-                    const int c = a.col[q];
-                    const double v = a.val[q];
-                    if (!HALO) {
-                        sum0 += v * __ldg(a.x0 + c);
-                        if (NV == 2) sum1 += v * __ldg(a.x1 + c);
-                    } else {
-                        sum0 += v * __ldcg((c < n_own ? a.x0 : h0) + c);
-                        if (NV == 2) sum1 += v * __ldcg((c < n_own ? a.x1 : h1) + c);
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    sum0 += __shfl_down_sync(0xffffffffu, sum0, off);
-                    if (NV == 2) sum1 += __shfl_down_sync(0xffffffffu, sum1, off);
-                }
-                if (lane == 0) {
-                    const long long row = r0 + r;
-                    finish_row(row, sum0, sum1, (FUSE == 0 && a.w) ? a.w[row] : 0.0, FUSE ? a.f_a[row] : 0.0,
-                               (FUSE == 1) ? a.f_b[row] : 0.0, FUSE ? a.f_x[row] : 0.0, FUSE ? a.x0[row] : 0.0);
-                }
-            }
-        }
+        // boundary tile of the fused exchange: the peers' entries must have landed before its halo columns are read
+        const bool bnd = HALO && tile >= tiles_a;
+        if (bnd && !halo_ready) wait_halo();
+        if (bnd) row_phase(std::true_type{}, staged, nr, r0, rp, rofs, q0, scol, sval);
+        else row_phase(std::false_type{}, staged, nr, r0, rp, rofs, q0, scol, sval);
         __syncthreads();   // everyone is done with stage s: thread 0 may refill it next iteration
     }
     if (HALO) {
-        // the last block to finish advances the consumed-exchange counter (every block read it at its start)
+        // The last block to leave advances the exchange counter (every block read it at its start) and re-arms the push
+        // ticket.  It must itself have seen the peers' flags: their arrival is what licenses the NEXT exchange to reuse
+        // the other bank at the peers, so a rank without boundary rows (pure sender) still consumes the flags here.
+        __shared__ int leave_last;
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            if (atomicAdd(a.hticket, 1u) == gridDim.x - 1) {
-                *a.hticket = 0u;
-                *a.hseq = hseq_next;
+            leave_last = (atomicAdd(a.hp->ticket_done, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (leave_last) {
+            if (!halo_ready) wait_halo();
+            if (tid == 0) {
+                *a.hp->ticket = 0u;
+                *a.hp->ticket_done = 0u;
+                *a.hp->seq = *a.hp->seq + 1ull;
+                __threadfence();
             }
         }
     }
@@ -620,66 +689,6 @@ __global__ void k_pattern_verify(const int32_t* __restrict__ rowptr, const int32
     }
 }
 
-// Owner-side halo push: store the entries each peer needs straight into that peer's receive buffer over NVLink, fence,
-// then (last block) raise the sequence flags.  Replaces pack kernel + ncclSend/ncclRecv + the side stream.
-__global__ void __launch_bounds__(256) k_halo_push(PkHaloPush hp, const double* __restrict__ x0,
-                                                   const double* __restrict__ x1, const PkState* st, int only_rollback,
-                                                   int dyn_cj) {
-    if (pk_done(st)) return;
-    if (only_rollback && *((volatile const int*)&st->rollback) == 0) return;
-    if (dyn_cj >= 0 && dyn_cj > *((volatile const int*)&st->k)) return;
-    const unsigned long long seq = *hp.seq + 1ull;
-    const int bank = (int)(seq & 1ull);
-    const long long total = hp.send_off[hp.n_ranks];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    constexpr int U = 4;                       // loads of U entries in flight before the remote stores
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
-        double v0[U], v1[U];
-        double* dst[U];
-        long long nh[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            dst[u] = nullptr;
-            if (i < total) {
-                int q = 0;
-                while (i >= hp.send_off[q + 1]) ++q;
-                const long long k = i - hp.send_off[q];
-                const long long src = hp.send_contig[q] ? (long long)hp.send_first[q] + k : (long long)hp.send_idx[i];
-                nh[u] = hp.peer_nhalo[q];
-                dst[u] = hp.peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh[u] + hp.dst_off[q] + k;
-                v0[u] = x0[src];
-                if (x1) v1[u] = x1[src];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (dst[u]) {
-                dst[u][0] = v0[u];
-                if (x1) dst[u][nh[u]] = v1[u];
-            }
-        }
-    }
-    __shared__ int is_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();      // cumulative: orders the whole block's remote stores (bar.sync above) before the ticket
-        is_last = (atomicAdd(hp.ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence_system();
-    if (threadIdx.x < hp.n_ranks && hp.send_off[threadIdx.x + 1] > hp.send_off[threadIdx.x]) {
-        volatile unsigned long long* f =
-            reinterpret_cast<volatile unsigned long long*>(hp.peer_recv[threadIdx.x]) + bank * PK_MAX_RANKS + hp.me;
-        *f = seq;
-    }
-    if (threadIdx.x == 0) {
-        *hp.ticket = 0u;
-        *hp.seq = seq;
-    }
-}
-
 // Dense row-major block: warp per row.
 struct GemvArgs {
     const double* A;
@@ -806,8 +815,11 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
     const size_t smem = stage_bytes * STAGES;
     const long long n_rows = a.row_hi - a.row_lo;
     const long long n_rows2 = a.row_hi2 > a.row_lo2 ? a.row_hi2 - a.row_lo2 : 0;
-    if (n_rows <= 0 && n_rows2 <= 0) { *grid_io = 0; return PK_OK; }
-    const long long n_tiles = (n_rows > 0 ? (n_rows + BLOCK - 1) / BLOCK : 0) + (n_rows2 + BLOCK - 1) / BLOCK;
+    const long long n_rows3 = a.row_hi3 > a.row_lo3 ? a.row_hi3 - a.row_lo3 : 0;
+    // a fused-exchange launch (HALO) runs even without rows: it still has to push and to consume the peers' flags
+    if (n_rows <= 0 && n_rows2 <= 0 && n_rows3 <= 0 && !HALO) { *grid_io = 0; return PK_OK; }
+    const long long n_tiles = (n_rows > 0 ? (n_rows + BLOCK - 1) / BLOCK : 0) + (n_rows2 + BLOCK - 1) / BLOCK +
+                              (n_rows3 + BLOCK - 1) / BLOCK;
     int grid = *grid_io;
     if (mode != 2) {
         const int per_sm = pk_blocks_per_sm((const void*)k_spmv_tma<NV, BLOCK, STAGES, HALO, FUSE>, BLOCK, smem);
@@ -1108,8 +1120,8 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.fuse = dots.fuse; a.cj = dots.cj; a.f_a = dots.f_a; a.f_b = dots.f_b; a.f_x = dots.f_x; a.f_out = dots.f_out;
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
-    a.row_lo2 = a.row_hi2 = 0;
-    a.hrecv = nullptr; a.hseq = nullptr; a.hticket = nullptr; a.n_own = m->n_rows; a.n_halo = m->n_halo; a.recv_mask = 0; a.n_ranks = ctx->n_ranks;
+    a.row_lo2 = a.row_hi2 = a.row_lo3 = a.row_hi3 = 0;
+    a.hrecv = nullptr; a.hp = nullptr; a.n_own = m->n_rows; a.n_halo = m->n_halo;
     a.cap = m->tile_cap;
     {
         static int ef = -1;
@@ -1126,43 +1138,16 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     if (!exchange) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
-    } else if (m->halo_p2p && m->use_tma && !ctx->nocomm) {
-        // NVLink push path, one stream: [push my boundary entries into the peers' receive buffers + flags] ->
-        // [interior rows] -> [boundary rows: wait for the peers' flags, read halo columns from the receive buffer].
-        seg_mark(ctx, 0);
-        {
-            // push on the side stream: it overlaps the interior rows; x must be complete first (event), and it must not
-            // be overwritten before the push has read it (the main stream waits for ev_b before the boundary rows)
-            const long long total = m->push.send_off[ctx->n_ranks];
-            int pg = (int)((total + 255) / 256);
-            if (pg > ctx->sm_count * 4) pg = ctx->sm_count * 4;
-            if (pg < 1) pg = 1;
-            PK_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-            PK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_a, 0));
-            k_halo_push<<<pg, 256, 0, ctx->side>>>(m->push, x, x1, ctx->d_state, ctx->ctl_only_rollback, ctx->ctl_dyn_cj);
-            PK_CUDA(cudaGetLastError());
-            PK_CUDA(cudaEventRecord(ctx->ev_b, ctx->side));
-            ctx->launches++;
-        }
-        seg_mark(ctx, 1);
-        const long long lo = m->interior_lo, hi = m->interior_hi;
-        const int cap_each = ctx->red.max_blocks / 2;
-        int g_int = 0, g_bnd = 0;
-        SpmvArgs ai = a, ab = a;
-        ai.row_lo = lo; ai.row_hi = hi;
-        ab.row_lo = 0; ab.row_hi = lo; ab.row_lo2 = hi; ab.row_hi2 = m->n_rows;
-        ab.hrecv = m->d_recvbuf; ab.hseq = m->push.recv_seq; ab.hticket = m->push.recv_ticket;
-        ab.recv_mask = m->push.recv_mask;
-        PK_CHECK(launch_stream_any(ctx, m, two, ai, ra, &g_int, cap_each, 1));
-        PK_CHECK(launch_stream_any(ctx, m, two, ab, ra, &g_bnd, cap_each, 1));
-        PkRedArgs r1 = ra, r2 = ra;
-        r1.block_off = 0; r1.nb_total = g_int + g_bnd; r1.store_only = (g_bnd > 0) ? 1 : 0;
-        r2.block_off = g_int; r2.nb_total = g_int + g_bnd; r2.store_only = 0;
-        if (g_int > 0) PK_CHECK(launch_stream_any(ctx, m, two, ai, r1, &g_int, cap_each, 2));
-        seg_mark(ctx, 2);
-        PK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
-        if (g_bnd > 0) PK_CHECK(launch_stream_any(ctx, m, two, ab, r2, &g_bnd, cap_each, 2));
-        seg_mark(ctx, 3);
+    } else if (m->halo_p2p && m->use_tma && !m->pat_on && !ctx->nocomm) {
+        // Exchange fused into the operator kernel (ONE launch, no NCCL, no side stream): every block pushes its share of
+        // my boundary entries into the peers' receive buffers over NVLink, the interior tiles run while the peers'
+        // pushes are in flight, the boundary tiles (scheduled last) wait for the peers' flags in-kernel.
+        a.row_lo = m->interior_lo; a.row_hi = m->interior_hi;
+        a.row_lo2 = 0; a.row_hi2 = m->interior_lo;
+        a.row_lo3 = m->interior_hi; a.row_hi3 = m->n_rows;
+        a.hrecv = m->d_recvbuf;
+        a.hp = m->d_push;
+        PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
     } else {
         // Interior rows (no halo column) run while the halo of x is in flight on the side stream; the boundary
         // rows follow the exchange.  All launches store partials into disjoint block slots of ONE reduction,

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Optional, Sequence
 
 import numpy as np
@@ -167,7 +168,10 @@ class DistOperator(Operator):
                                               ro.ctypes.data_as(C.c_void_p), _ptr(send_idx_d),
                                               C.c_void_p(send_idx_h.data_ptr()), plan["interior"][0],
                                               plan["interior"][1]), "pk_mat_set_halo")
-                if ctx.fused_allreduce and os.environ.get("PK_HALO", "nccl") == "p2p":
+                # default: halo exchange fused into the SpMV kernel over NVLink peer memory; PK_HALO=nccl keeps
+                # ncclSend/ncclRecv on a side stream (also the fallback when the peers' buffers cannot be mapped)
+                op.halo_path = "nccl"
+                if ctx.fused_allreduce and os.environ.get("PK_HALO", "p2p") != "nccl":
                     op._open_halo_push(group, world, rank, plan)
         return op
 
@@ -192,8 +196,13 @@ class DistOperator(Operator):
                                           nhalo.ctypes.data_as(C.c_void_p))
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=cdev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) != 1:
-            raise PkError("peer mapping of the halo receive buffers failed on some rank; set PK_HALO=nccl")
+        if int(ok.item()) != 1:                      # all ranks must take the same path
+            check(ctx.lib.pk_mat_halo_p2p_disable(self.handle), "pk_mat_halo_p2p_disable")
+            if rank == 0:
+                print("parallel_krylov_b200: peer mapping of the halo receive buffers failed on some rank; "
+                      "using the NCCL halo exchange", file=sys.stderr)
+        else:
+            self.halo_path = "p2p"
 
     @classmethod
     def from_local_dense(cls, local_a: torch.Tensor, group=None, ctx: Optional[Context] = None) -> "DistOperator":

@@ -59,6 +59,56 @@ def main():
                 assert info["converged"]
             except AssertionError as e:
                 failures.append(f"{tag} {e!r}"[:400])
+    # ---- structurally nonsymmetric A (upper block triangular across the ranks): the last rank references no remote column
+    # but its rows are needed by its predecessor -> a pure sender must still send / push, and must be throttled by its
+    # receiver during the back-to-back basis SpMVs of the k-skip variants
+    import scipy.sparse as sp
+    n = 20011
+    tri = sp.diags([np.full(n, 4.0), np.full(n - 1, -1.0), np.full(n - 7, -0.5), np.full(n - 40, -0.25)], [0, 1, 7, 40],
+                   format="csr")
+    base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
+    b = problems.rhs(n, "randn", 0)
+    # (the k-skip recurrences assume a symmetric A — the reference itself diverges on this system — so: MrR, plus chained
+    # two-vector operator applications with NO reduction in between, the pattern of the k-skip basis)
+    xo, io = oracle.mrr(tri, b.copy(), tol=1e-8)
+    x, info = pkm.mrr(None, tri[lo:hi], b, tol=1e-8)
+    res = info["residual"].cpu().numpy()
+    try:
+        assert abs(int(info["nosl"][-1]) - int(io["nosl"][-1])) <= 2, (int(info["nosl"][-1]), int(io["nosl"][-1]))
+        m = min(len(res), len(io["residual"]))
+        np.testing.assert_allclose(res[:m], io["residual"][:m], rtol=1e-10)
+        assert oracle.true_relres(tri, b, x.cpu().numpy()) < 1e-8 * (1 + 1e-6)
+    except AssertionError as e:
+        failures.append(f"[upper-triangular mrr rank {rank}] {e!r}"[:400])
+    op = pkm.DistOperator.from_any_local(tri[lo:hi], None)
+    v0, v1 = b.copy(), np.cos(np.arange(n, dtype=np.float64))
+    u0 = torch.from_numpy(v0[lo:hi]).cuda()
+    u1 = torch.from_numpy(v1[lo:hi]).cuda()
+    for _ in range(24):                              # 24 exchanges back to back, both vectors per exchange
+        u0, u1 = op.matvec(u0, x1=u1)
+        u0, u1 = u0 * 0.25, u1 * 0.25
+        v0, v1 = tri.dot(v0) * 0.25, tri.dot(v1) * 0.25
+    if not (np.array_equal(u0.cpu().numpy(), v0[lo:hi]) and np.array_equal(u1.cpu().numpy(), v1[lo:hi])):
+        failures.append(f"[upper-triangular chained two-vector SpMV rank {rank}] differs from scipy (must be bit-identical)")
+    del op
+
+    # ---- uneven blocks of ~1.0 M and ~1.4 M rows (2 ranks): the host's poll batch must be the same on every rank, or the
+    # host-enqueued collectives of the NCCL paths lose their partner and the solve hangs
+    if world == 2:
+        A = problems.to_scipy(*problems.poisson3d(134))
+        n = A.shape[0]
+        cut = 1_000_000
+        lo, hi = (0, cut) if rank == 0 else (cut, n)
+        b = problems.rhs(n, "randn", 0)
+        xo, io = oracle.cg(A, b.copy(), tol=1e-8, maxiter=60)
+        x, info = pkm.cg(None, A[lo:hi], b, tol=1e-8, maxiter=60)
+        res = info["residual"].cpu().numpy()
+        try:
+            assert int(info["nosl"][-1]) == int(io["nosl"][-1]) == 60
+            np.testing.assert_allclose(res[:50], io["residual"][:50], rtol=1e-10)
+        except AssertionError as e:
+            failures.append(f"[uneven 1.0M/1.4M rank {rank}] {e!r}"[:400])
+
     # a vector given as this rank's slice only, an initial guess, and gather_x=False
     A = mats["p3d20"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
     b = problems.rhs(n, "randn", 0); x0 = np.random.default_rng(3).standard_normal(n)
@@ -74,7 +124,8 @@ def main():
     for f in failures:
         print("FAIL", f, flush=True)
     if rank == 0:
-        print("DIST_PARITY", "OK" if flag.item() == 0 else f"FAILED ({int(flag.item())})", f"world={world}", flush=True)
+        print("DIST_PARITY", "OK" if flag.item() == 0 else f"FAILED ({int(flag.item())})", f"world={world}",
+              f"halo={os.environ.get('PK_HALO', 'p2p')} allreduce={os.environ.get('PK_ALLREDUCE', 'p2p')}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 0 else 1)

@@ -1,5 +1,5 @@
 """Model check (CPU) of the two NVLink protocols used inside the kernels — the mailbox all-reduce
-(csrc/pk_device.cuh: pk_grid_reduce) and the halo push (csrc/pk_spmv.cu: k_halo_push + the HALO kernel) — under random
+(csrc/pk_device.cuh: pk_grid_reduce) and the halo push fused into the SpMV kernel (csrc/pk_spmv.cu: k_spmv_tma<HALO>) — under random
 interleavings of the ranks' steps.  The model keeps the features the correctness argument rests on: two banks selected
 by sequence parity, payload stores ordered before the flag store, readers that only read after seeing their flags, and
 no other synchronisation between ranks.  Checked: every rank obtains exactly the sum / halo of the right sequence number
@@ -58,41 +58,45 @@ def test_mailbox_allreduce_two_banks_suffice(P):
             assert results[r] == want
 
 
-def _halo_rank(me, P, recv, n_rounds, data, got):
-    """One rank of a ring: push my boundary to both neighbours (side stream), interior work, then the boundary kernel
-    waits for the neighbours' flags of THIS exchange and reads their data; the next push is ordered after that kernel
-    (event) exactly as in spmv_impl()."""
-    nbrs = [q for q in ((me - 1) % P, (me + 1) % P) if q != me]
-    nbrs = sorted(set(nbrs))
+def _halo_rank(me, P, recv, n_rounds, data, got, sends, symmetric_flags=True):
+    """One rank's SpMV kernels with the exchange fused in (csrc/pk_spmv.cu: k_spmv_tma<HALO>): at its start the kernel
+    pushes my entries to the ranks that need them and then raises its flag at EVERY peer (any rank it exchanges with in
+    either direction); interior tiles; before the boundary tiles — or, without boundary rows, before the kernel ends — it
+    waits for the flag of THIS exchange from every peer, then reads the entries sent to it.  `sends[r]` = ranks r sends
+    to (arbitrary, possibly one-directional).  symmetric_flags=False models the flawed variant where flags only follow
+    the data (a pure sender is then never throttled by its receiver)."""
+    to = sorted(sends[me])
+    frm = sorted(q for q in range(P) if me in sends[q])
+    peers = sorted(set(to) | set(frm))
+    flag_to = peers if symmetric_flags else to
+    wait_from = peers if symmetric_flags else frm
     for seq in range(1, n_rounds + 1):
         bank = seq & 1
-        for q in nbrs:                              # k_halo_push: data, fence, flag
+        for q in to:                                # push: data ...
             recv[q][bank][me]["data"] = (seq, data[me][seq])
             yield
-        for q in nbrs:
+        for q in flag_to:                           # ... fence, flags
             recv[q][bank][me]["flag"] = seq
             yield
-        for _ in range(3):                          # interior rows
+        for _ in range(3):                          # interior tiles
             yield
-        for q in nbrs:                              # boundary kernel: wait, then read
+        for q in wait_from:                         # boundary tiles (or kernel exit): wait, then read
             while recv[me][bank][q]["flag"] != seq:
                 yield
-        for q in nbrs:
+        for q in frm:
             s, val = recv[me][bank][q]["data"]
             assert s == seq, f"rank {me} read halo of exchange {s} during exchange {seq}"
             got[me].append((seq, q, val))
             yield
 
 
-@pytest.mark.parametrize("P", [2, 4, 8])
-def test_halo_push_two_banks_suffice(P):
-    rng = random.Random(100 + P)
-    for trial in range(300):
+def _run_halo_model(P, sends, rng, symmetric_flags=True, trials=300):
+    for trial in range(trials):
         n_rounds = 10
         data = [[rng.randrange(1000) for _ in range(n_rounds + 1)] for _ in range(P)]
         recv = [[[{"data": (0, 0), "flag": 0} for _ in range(P)] for _ in range(2)] for _ in range(P)]
         got = [[] for _ in range(P)]
-        gens = [_halo_rank(r, P, recv, n_rounds, data, got) for r in range(P)]
+        gens = [_halo_rank(r, P, recv, n_rounds, data, got, sends, symmetric_flags) for r in range(P)]
         alive = list(range(P))
         fav = rng.randrange(P)
         steps = 0
@@ -107,6 +111,32 @@ def test_halo_push_two_banks_suffice(P):
         for r in range(P):
             for seq, q, val in got[r]:
                 assert val == data[q][seq]
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_halo_push_two_banks_suffice(P):
+    """Symmetric neighbour exchange (slabs, bands): a ring."""
+    ring = [sorted({(r - 1) % P, (r + 1) % P} - {r}) for r in range(P)]
+    _run_halo_model(P, ring, random.Random(100 + P))
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+def test_halo_push_one_directional_patterns(P):
+    """Structurally nonsymmetric A (block triangular): rank r only SENDS to r+1 and rank P-1 has no boundary rows to feed
+    anyone.  Flags in both directions keep a pure sender at most one exchange ahead of its receiver; random digraphs too."""
+    chain = [[r + 1] if r + 1 < P else [] for r in range(P)]
+    _run_halo_model(P, chain, random.Random(200 + P))
+    rng = random.Random(300 + P)
+    for _ in range(10):
+        sends = [[q for q in range(P) if q != r and rng.random() < 0.4] for r in range(P)]
+        _run_halo_model(P, sends, rng, trials=30)
+
+
+def test_model_detects_the_unthrottled_pure_sender():
+    """Sanity of the model: if flags only follow the data, a pure sender runs two exchanges ahead and overwrites a bank
+    its receiver is still reading (the hazard ADVICE r01 named)."""
+    with pytest.raises(AssertionError):
+        _run_halo_model(2, [[1], []], random.Random(7), symmetric_flags=False, trials=200)
 
 
 def test_model_detects_the_single_bank_hazard():
