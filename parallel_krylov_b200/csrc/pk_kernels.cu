@@ -125,7 +125,39 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mrr_update(long long n, const doub
     const double eta = (cj < 0) ? ra.st->eta : ra.st->coef[2 * cj + 1];
     double acc[1] = {0.0};
     const long long stride = (long long)gridDim.x * EW_BLOCK;
-    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+    // Nine streams (5 loads, 4 stores) per element: with one element per thread the kernel reached 76 % of HBM peak;
+    // 128-bit accesses (two elements per thread) halve the number of memory instructions in flight per byte.
+    const bool vec = ((((uintptr_t)ar | (uintptr_t)y | (uintptr_t)z | (uintptr_t)r | (uintptr_t)r_out | (uintptr_t)x) & 15) == 0);
+    long long done_to = 0;
+    if (vec) {
+        const long long n2 = n >> 1;
+        const double2* ar2 = reinterpret_cast<const double2*>(ar);
+        const double2* r2 = reinterpret_cast<const double2*>(r);
+        double2* y2 = reinterpret_cast<double2*>(y);
+        double2* z2 = reinterpret_cast<double2*>(z);
+        double2* ro2 = reinterpret_cast<double2*>(r_out);
+        double2* x2 = reinterpret_cast<double2*>(x);
+        for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n2; i += stride) {
+            const double2 rv = r2[i], yv = y2[i], av = ar2[i], zv = z2[i], xv = x2[i];
+            double2 yo, zo, ro, xo;
+            yo.x = eta * yv.x + zeta * av.x;
+            yo.y = eta * yv.y + zeta * av.y;
+            zo.x = eta * zv.x - zeta * rv.x;
+            zo.y = eta * zv.y - zeta * rv.y;
+            ro.x = rv.x - yo.x;
+            ro.y = rv.y - yo.y;
+            xo.x = xv.x - zo.x;
+            xo.y = xv.y - zo.y;
+            y2[i] = yo;
+            z2[i] = zo;
+            ro2[i] = ro;
+            x2[i] = xo;
+            acc[0] += ro.x * ro.x;
+            acc[0] += ro.y * ro.y;
+        }
+        done_to = n2 << 1;
+    }
+    for (long long i = done_to + (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
         double ri = r[i];
         double yi = eta * y[i] + zeta * ar[i];
         double zi = eta * z[i] - zeta * ri;

@@ -188,11 +188,13 @@ struct TileMeta {
     int pad;
 };
 
-// Resident blocks per SM the fused-exchange variants are compiled for: the same as their plain counterparts reach (4 for
-// the single-vector SpMV with 256-row tiles, 3 for the two-chain and fused-step forms), so that a rank of a multi-GPU
-// run streams A with as many bulk copies in flight as a single GPU does.
+// Resident blocks per SM the fused-exchange (HALO) variants with 256-row tiles are compiled for: 4 for the single-vector
+// SpMV, 3 for the two-chain and fused-step forms — what their plain counterparts reach on their own — so that a rank of a
+// multi-GPU run streams A with as many bulk copies in flight as a single GPU does.  0 = no constraint (plain variants;
+// 128-row tiles are limited by shared memory).  NB: a constraint of 1 is NOT neutral — ptxas then spends 101 registers
+// on the plain SpMV, which halves its occupancy and costs 28 % of its bandwidth (measured, r02).
 template <int NV, int BLOCK, bool HALO, int FUSE>
-constexpr int spmv_min_blocks() { return (HALO && BLOCK == 256) ? ((NV == 1 && FUSE == 0) ? 4 : 3) : 1; }
+constexpr int spmv_min_blocks() { return (HALO && BLOCK == 256) ? ((NV == 1 && FUSE == 0) ? 4 : 3) : 0; }
 
 template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
 __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>()) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
@@ -703,57 +705,93 @@ struct GemvArgs {
     int vec;               // rows 16-byte aligned: double2 loads
 };
 
+// A warp owns R = 4 consecutive rows at a time: every x (and x1) element it loads is used for 4 rows from registers, so
+// the vector traffic through L1/L2 is a quarter of the one-row-per-warp form (with two right-hand sides the two vectors
+// no longer fit L1 next to each other and the old kernel was L2-bound at 55 % of HBM peak), and 4 independent 128-bit
+// loads of A are in flight per lane and iteration.  Per row the lane partition and the order of additions are unchanged
+// (lane l sums columns 2l, 2l+1, 2l+64, ... then the shuffle tree), so results are bit-identical to the one-row form.
 template <int NV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_gemv(GemvArgs a, PkRedArgs ra) {
     if (pk_skip(ra)) return;
     constexpr int NW = BLOCK / 32;
+    constexpr int R = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[3] = {0.0, 0.0, 0.0};
-    for (long long row = (long long)blockIdx.x * NW + warp; row < a.n_rows; row += (long long)gridDim.x * NW) {
-        const double* ar = a.A + row * a.lda;
-        double s0 = 0.0, s1 = 0.0;
+    const long long n_groups = (a.n_rows + R - 1) / R;
+    for (long long g = (long long)blockIdx.x * NW + warp; g < n_groups; g += (long long)gridDim.x * NW) {
+        const long long row0 = g * R;
+        const double* ar[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = row0 + r < a.n_rows ? row0 + r : a.n_rows - 1;     // clamp: tail rows are discarded below
+            ar[r] = a.A + row * a.lda;
+        }
+        double s0[R], s1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { s0[r] = 0.0; s1[r] = 0.0; }
         if (a.vec) {
             const long long n2 = a.n_cols >> 1;
-            const double2* ar2 = reinterpret_cast<const double2*>(ar);
             const double2* x02 = reinterpret_cast<const double2*>(a.x0);
             const double2* x12 = reinterpret_cast<const double2*>(a.x1);
-#pragma unroll 4
+#pragma unroll 2
             for (long long c = lane; c < n2; c += 32) {
-                const double2 av = __ldg(ar2 + c);
+                double2 av[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) av[r] = __ldg(reinterpret_cast<const double2*>(ar[r]) + c);
                 const double2 xv = __ldg(x02 + c);
-                s0 += av.x * xv.x;
-                s0 += av.y * xv.y;
-                if (NV == 2) {
-                    const double2 xw = __ldg(x12 + c);
-                    s1 += av.x * xw.x;
-                    s1 += av.y * xw.y;
+                double2 xw = make_double2(0.0, 0.0);
+                if (NV == 2) xw = __ldg(x12 + c);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    s0[r] += av[r].x * xv.x;
+                    s0[r] += av[r].y * xv.y;
+                    if (NV == 2) {
+                        s1[r] += av[r].x * xw.x;
+                        s1[r] += av[r].y * xw.y;
+                    }
                 }
             }
             if ((a.n_cols & 1) && lane == 0) {
                 const long long c = a.n_cols - 1;
-                s0 += ar[c] * a.x0[c];
-                if (NV == 2) s1 += ar[c] * a.x1[c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    s0[r] += ar[r][c] * a.x0[c];
+                    if (NV == 2) s1[r] += ar[r][c] * a.x1[c];
+                }
             }
         } else {
             for (long long c = lane; c < a.n_cols; c += 32) {
-                const double av = ar[c];
-                s0 += av * a.x0[c];
-                if (NV == 2) s1 += av * a.x1[c];
+                const double xv = a.x0[c];
+                const double xw = (NV == 2) ? a.x1[c] : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double av = ar[r][c];
+                    s0[r] += av * xv;
+                    if (NV == 2) s1[r] += av * xw;
+                }
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            s0 += __shfl_down_sync(0xffffffffu, s0, off);
-            if (NV == 2) s1 += __shfl_down_sync(0xffffffffu, s1, off);
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s0[r] += __shfl_down_sync(0xffffffffu, s0[r], off);
+                if (NV == 2) s1[r] += __shfl_down_sync(0xffffffffu, s1[r], off);
+            }
         }
         if (lane == 0) {
-            a.y0[row] = s0;
-            if (NV == 2) a.y1[row] = s1;
-            if (a.w) {
-                const double wi = a.w[row];
-                acc[0] += wi * s0;
-                acc[1] += s0 * s0;
-                acc[2] += wi * wi;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long row = row0 + r;
+                if (row >= a.n_rows) break;
+                a.y0[row] = s0[r];
+                if (NV == 2) a.y1[row] = s1[r];
+                if (a.w) {
+                    const double wi = a.w[row];
+                    acc[0] += wi * s0[r];
+                    acc[1] += s0[r] * s0[r];
+                    acc[2] += wi * wi;
+                }
             }
         }
     }
@@ -914,7 +952,7 @@ int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRed
 
 int launch_gemv(pk_ctx* ctx, pk_mat* m, bool two, const GemvArgs& a, PkRedArgs ra) {
     constexpr int BLOCK = 256;
-    long long want = (a.n_rows + (BLOCK / 32) - 1) / (BLOCK / 32);
+    long long want = ((a.n_rows + 3) / 4 + (BLOCK / 32) - 1) / (BLOCK / 32);      // a warp takes 4 rows at a time
     long long cap = (long long)ctx->sm_count *
                     pk_blocks_per_sm(two ? (const void*)k_gemv<2, BLOCK> : (const void*)k_gemv<1, BLOCK>, BLOCK, 0);
     if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;

@@ -1,0 +1,52 @@
+"""Register / spill budget of the hot kernels, read from the ptxas -v log of the in-tree build (CPU test).
+
+The persistent grids are sized `SMs x resident blocks`; a kernel that silently grows past its register budget loses a
+resident block per SM and a quarter of its bandwidth (r02: a `__launch_bounds__(256, 1)` on the plain SpMV made ptxas
+spend 101 registers instead of 64 and cost 28 %).  This pins the budgets the measured numbers were taken with."""
+import os
+import re
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LOGDIR = os.path.join(HERE, "..", "parallel_krylov_b200", "csrc", "build")
+
+
+def _resources(log):
+    path = os.path.join(LOGDIR, log)
+    if not os.path.exists(path):
+        pytest.skip(f"{log} not found (library not built in-tree)")
+    txt = open(path).read()
+    out = {}
+    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'.*?(\d+) bytes stack frame, (\d+) bytes spill stores.*?"
+                         r"Used (\d+) registers", txt, flags=re.S):
+        out[m.group(1)] = (int(m.group(4)), int(m.group(3)))
+    return out
+
+
+def _find(res, pattern):
+    hits = [(k, v) for k, v in res.items() if re.search(pattern, k)]
+    assert hits, pattern
+    return hits
+
+
+def test_spmv_register_budgets():
+    res = _resources("pk_spmv.cu.log")
+    # plain single-vector SpMV, 256-row tiles: 64 registers, no spills -> 4 blocks / SM
+    for stages in (2, 3, 4):
+        for name, (regs, spill) in _find(res, rf"k_spmv_tmaILi1ELi256ELi{stages}ELb0ELi0E"):
+            assert regs <= 64 and spill == 0, (name, regs, spill)
+    # fused-exchange variant of the same kernel must also fit 4 blocks / SM
+    for name, (regs, spill) in _find(res, r"k_spmv_tmaILi1ELi256ELi2ELb1ELi0E"):
+        assert regs <= 64, (name, regs, spill)
+    # two-chain and fused-step forms: 3 blocks / SM (<= 85 registers), plain and fused-exchange
+    for pat in (r"k_spmv_tmaILi2ELi256ELi2ELb[01]ELi0E", r"k_spmv_tmaILi1ELi256ELi2ELb[01]ELi[12]E"):
+        for name, (regs, spill) in _find(res, pat):
+            assert regs <= 85, (name, regs, spill)
+
+
+def test_vector_kernel_register_budgets():
+    res = _resources("pk_kernels.cu.log")
+    for pat, cap in ((r"k_cg_xr", 40), (r"k_cg_pE", 32), (r"k_mrr_update", 64)):
+        for name, (regs, spill) in _find(res, pat):
+            assert regs <= cap, (name, regs, spill)
