@@ -56,6 +56,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
 // peer is a few microseconds behind); after that the thread backs off with nanosleep so that a long wait does not
 // hammer L2, and the wall-clock budget (PK_SPIN_TIMEOUT_NS of %globaltimer, not a poll count) bounds a wait for a peer
 // that died: the caller then stops the solve with an error instead of hanging the GPU.
+// acquire/release fence at system scope (orders this thread's accesses to peer GPUs' memory).  __threadfence_system() is
+// the sequentially-consistent flavour (SASS MEMBAR.SC.SYS), which every block of a persistent grid executing once costs
+// hundreds of microseconds in total (measured, r02); the protocols here only need release / acquire ordering.
+__device__ __forceinline__ void pk_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 constexpr unsigned long long PK_SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ unsigned long long pk_globaltimer() {
     unsigned long long t;
@@ -181,9 +186,9 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
             const int p = t / n, j = t - p * n;
             pp->mbox[p][((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + j] = buf[j];
         }
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x < P) {
+            pk_fence_sys();                           // release: cumulative over the block's payload stores (barrier above)
             volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
                 pp->mbox[threadIdx.x] + ((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
             *f = seq;
@@ -194,9 +199,9 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
                 ra.st->converged = 0;
                 ra.st->guard = -1;
             }
+            pk_fence_sys();                           // acquire: the payload behind the flag is visible ...
         }
-        __threadfence_system();
-        __syncthreads();
+        __syncthreads();                              // ... to the whole block
         for (int j = threadIdx.x; j < n; j += BLOCK) {
             double v = 0.0;
             for (int p = 0; p < P; ++p)

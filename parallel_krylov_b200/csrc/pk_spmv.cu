@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra)
 // i+STAGES-1 while all threads run the row phase of tile i, so HBM requests stay in flight regardless of how long the
 // row phase takes; the CSR arrays never pass through registers.  A tile that cannot be bulk-copied (window crosses the
 // end of the arrays, or longer than the stage: long rows) is fetched/processed by the plain paths below.
+constexpr int PK_PUSH_BLOCKS = 32;   // blocks of the fused-exchange SpMV that push the boundary entries to the peers
+
 struct TileMeta {
     int q0;       // first staged nonzero (16-byte aligned index)
     int ra0;      // first staged rowptr entry (aligned row index, relative to the range: may be < r0)
@@ -317,39 +319,61 @@ __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>(
             const volatile unsigned long long* f =
                 reinterpret_cast<const volatile unsigned long long*>(a.hrecv) + (int)(hseq & 1ull) * PK_MAX_RANKS + tid;
             if (!pk_spin_until(f, hseq)) { ra.st->done = 1; ra.st->converged = 0; ra.st->guard = -2; }
+            pk_fence_sys();            // acquire: the entries the flag announces are visible to this thread ...
         }
-        __threadfence_system();
-        __syncthreads();
+        __syncthreads();               // ... and, through the barrier, to the whole block
         halo_ready = true;
     };
     if (HALO) {
         const PkHaloPush* hp = a.hp;
-        const unsigned long long hseq = *hp->seq + 1ull;
-        const int bank = (int)(hseq & 1ull);
-        const int P = hp->n_ranks;
-        const long long total = hp->send_off[P];
-        const long long stride = (long long)gridDim.x * BLOCK;
-        for (long long i = (long long)blockIdx.x * BLOCK + tid; i < total; i += stride) {
-            int q = 0;
-            while (i >= hp->send_off[q + 1]) ++q;
-            const long long kq = i - hp->send_off[q];
-            const long long src = hp->send_contig[q] ? (long long)hp->send_first[q] + kq : (long long)hp->send_idx[i];
-            const long long nh = hp->peer_nhalo[q];
-            double* dst = hp->peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh + hp->dst_off[q] + kq;
-            dst[0] = a.x0[src];
-            if (NV == 2) dst[nh] = a.x1[src];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();      // cumulative: orders the whole block's remote stores (bar.sync above) before the ticket
-            push_last = (atomicAdd(hp->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-        }
-        __syncthreads();
-        if (push_last) {
-            // every block's entries are on their way: raise this exchange's flag at every peer I talk to (also the ones
-            // that only send to me — the flag is their licence to reuse this bank two exchanges from now)
-            __threadfence_system();
-            if (tid < P && ((hp->peer_mask >> tid) & 1u)) {
+        // The first PK_PUSH_BLOCKS blocks push (a few thousand entries each: 2 x 2 MiB planes at 512^3 / 8 ranks); the
+        // others go straight to their tiles.  Every pushing block pays one system-scope fence before it may count
+        // itself done — with ALL ~600 blocks pushing, those fences alone cost ~250 us per SpMV (measured, r02).
+        const unsigned int n_push = gridDim.x < (unsigned)PK_PUSH_BLOCKS ? gridDim.x : (unsigned)PK_PUSH_BLOCKS;
+        if (blockIdx.x < n_push) {
+            const unsigned long long hseq = *hp->seq + 1ull;
+            const int bank = (int)(hseq & 1ull);
+            const int P = hp->n_ranks;
+            const long long total = hp->send_off[P];
+            const long long stride = (long long)n_push * BLOCK;
+            constexpr int U = 4;                   // loads of U entries in flight before the remote stores
+            for (long long i0 = (long long)blockIdx.x * BLOCK + tid; i0 < total; i0 += U * stride) {
+                double v0[U], v1[U];
+                double* dst[U];
+                long long nh[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long i = i0 + u * stride;
+                    dst[u] = nullptr;
+                    if (i < total) {
+                        int q = 0;
+                        while (i >= hp->send_off[q + 1]) ++q;
+                        const long long kq = i - hp->send_off[q];
+                        const long long src = hp->send_contig[q] ? (long long)hp->send_first[q] + kq : (long long)hp->send_idx[i];
+                        nh[u] = hp->peer_nhalo[q];
+                        dst[u] = hp->peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh[u] + hp->dst_off[q] + kq;
+                        v0[u] = a.x0[src];
+                        if (NV == 2) v1[u] = a.x1[src];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (dst[u]) {
+                        dst[u][0] = v0[u];
+                        if (NV == 2) dst[u][nh[u]] = v1[u];
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                pk_fence_sys();          // release, cumulative over the block's remote stores (bar.sync above)
+                push_last = (atomicAdd(hp->ticket, 1u) == n_push - 1) ? 1 : 0;
+            }
+            __syncthreads();
+            if (push_last && tid < P && ((hp->peer_mask >> tid) & 1u)) {
+                // every pushing block's entries are on their way: raise this exchange's flag at every peer I talk to (also
+                // the ones that only send to me — the flag is their licence to reuse this bank two exchanges from now)
+                pk_fence_sys();
                 volatile unsigned long long* f =
                     reinterpret_cast<volatile unsigned long long*>(hp->peer_recv[tid]) + bank * PK_MAX_RANKS + hp->me;
                 *f = hseq;
@@ -798,6 +822,111 @@ __global__ void __launch_bounds__(BLOCK) k_gemv(GemvArgs a, PkRedArgs ra) {
     if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
 }
 
+// Two right-hand sides: x0 and x1 together (2 x 8 n_cols bytes) no longer fit L1 next to each other, every warp walks
+// the vectors at its own pace, and the kernel above becomes L2-bound (55 % of HBM peak at 16384^2).  Here the block's
+// warps walk the columns TOGETHER: the current chunk of x0 / x1 is staged in shared memory by bulk copies (2-stage ring,
+// one mbarrier per stage, issued by one thread while the previous chunk is consumed) and every warp reads it from there
+// for its 4 rows.  Per row, the lane partition and the order of additions are those of k_gemv (bit-identical results).
+template <int NV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_gemv_staged(GemvArgs a, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    constexpr int NW = BLOCK / 32;
+    constexpr int R = 4;
+    constexpr int CW = 2048;                        // columns per chunk (16 KB per vector and stage)
+    constexpr int STAGES = 2;
+    extern __shared__ __align__(128) unsigned char gsm_raw[];
+    double* xs = reinterpret_cast<double*>(gsm_raw);                 // [STAGES][NV][CW]
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const long long n_groups = (a.n_rows + (long long)R * NW - 1) / ((long long)R * NW);    // 32 rows per block and pass
+    const long long n_chunks = (a.n_cols + CW - 1) / CW;
+    const long long my_groups = n_groups > blockIdx.x ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total = my_groups * n_chunks;                    // chunk visits of this block
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long v) {                                  // thread 0: chunk visit v -> stage v % STAGES
+        const int s = (int)(v % STAGES);
+        const long long c0 = (v % n_chunks) * CW;
+        const unsigned bytes = (unsigned)((a.n_cols - c0 < CW ? a.n_cols - c0 : CW) * sizeof(double));
+        mbar_expect_tx(&full[s], bytes * NV);
+        bulk_g2s(xs + ((size_t)s * NV + 0) * CW, a.x0 + c0, bytes, &full[s]);
+        if (NV == 2) bulk_g2s(xs + ((size_t)s * NV + 1) * CW, a.x1 + c0, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (long long v = 0; v < STAGES - 1 && v < total; ++v) issue(v);
+    long long v = 0;
+    for (long long gi = 0; gi < my_groups; ++gi) {
+        const long long g = blockIdx.x + gi * (long long)gridDim.x;
+        const long long row0 = (g * NW + warp) * R;
+        const double2* ar2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = row0 + r < a.n_rows ? row0 + r : a.n_rows - 1;     // clamp: tail rows are discarded below
+            ar2[r] = reinterpret_cast<const double2*>(a.A + row * a.lda);
+        }
+        double s0[R], s1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { s0[r] = 0.0; s1[r] = 0.0; }
+        for (long long ch = 0; ch < n_chunks; ++ch, ++v) {
+            const int s = (int)(v % STAGES);
+            if (tid == 0 && v + STAGES - 1 < total) issue(v + STAGES - 1);
+            mbar_wait(&full[s], (unsigned)((v / STAGES) & 1));
+            const long long c0 = ch * CW;
+            const int w2 = (int)((a.n_cols - c0 < CW ? a.n_cols - c0 : CW) >> 1);    // double2 elements in this chunk
+            const double2* x02 = reinterpret_cast<const double2*>(xs + ((size_t)s * NV + 0) * CW);
+            const double2* x12 = reinterpret_cast<const double2*>(xs + ((size_t)s * NV + 1) * CW);
+            const long long cb = c0 >> 1;
+#pragma unroll 2
+            for (int c = lane; c < w2; c += 32) {
+                double2 av[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) av[r] = __ldg(ar2[r] + cb + c);
+                const double2 xv = x02[c];
+                double2 xw = make_double2(0.0, 0.0);
+                if (NV == 2) xw = x12[c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    s0[r] += av[r].x * xv.x;
+                    s0[r] += av[r].y * xv.y;
+                    if (NV == 2) {
+                        s1[r] += av[r].x * xw.x;
+                        s1[r] += av[r].y * xw.y;
+                    }
+                }
+            }
+            __syncthreads();          // the stage may be refilled by the next visit's issue
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s0[r] += __shfl_down_sync(0xffffffffu, s0[r], off);
+                if (NV == 2) s1[r] += __shfl_down_sync(0xffffffffu, s1[r], off);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long row = row0 + r;
+                if (row >= a.n_rows) break;
+                a.y0[row] = s0[r];
+                if (NV == 2) a.y1[row] = s1[r];
+                if (a.w) {
+                    const double wi = a.w[row];
+                    acc[0] += wi * s0[r];
+                    acc[1] += s0[r] * s0[r];
+                    acc[2] += wi * wi;
+                }
+            }
+        }
+    }
+    if (a.reduce) pk_grid_reduce<3, BLOCK>(acc, ra);
+}
+
 template <int NV, int BLOCK, bool VEC>
 int stream_grid(pk_ctx* ctx, size_t smem, long long n_tiles) {
     const int per_sm = pk_blocks_per_sm((const void*)k_spmv_stream<NV, BLOCK, VEC>, BLOCK, smem);
@@ -952,20 +1081,39 @@ int launch_stream_any(pk_ctx* ctx, pk_mat* m, bool two, const SpmvArgs& a, PkRed
 
 int launch_gemv(pk_ctx* ctx, pk_mat* m, bool two, const GemvArgs& a, PkRedArgs ra) {
     constexpr int BLOCK = 256;
-    long long want = ((a.n_rows + 3) / 4 + (BLOCK / 32) - 1) / (BLOCK / 32);      // a warp takes 4 rows at a time
-    long long cap = (long long)ctx->sm_count *
-                    pk_blocks_per_sm(two ? (const void*)k_gemv<2, BLOCK> : (const void*)k_gemv<1, BLOCK>, BLOCK, 0);
-    if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
-    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-    if (two) k_gemv<2, BLOCK><<<grid, BLOCK, 0, ctx->stream>>>(a, ra);
-    else k_gemv<1, BLOCK><<<grid, BLOCK, 0, ctx->stream>>>(a, ra);
+    (void)m;
+    static int staged_mode = -1;                  // PK_GEMV=plain: never stage x; staged: also for one right-hand side
+    if (staged_mode < 0) {
+        const char* e = getenv("PK_GEMV");
+        staged_mode = (e && strcmp(e, "plain") == 0) ? 0 : ((e && strcmp(e, "staged") == 0) ? 2 : 1);
+    }
+    // x staged in shared memory: pays when the vectors do not fit L1 (two right-hand sides, long rows); needs 16-byte
+    // aligned rows and an even number of columns (bulk copies move multiples of 16 bytes)
+    const bool staged = a.vec && (a.n_cols & 1) == 0 && a.n_cols >= 4096 && (staged_mode == 2 || (staged_mode == 1 && two));
+    if (staged) {
+        const size_t smem = (size_t)2 * (two ? 2 : 1) * 2048 * sizeof(double);
+        const void* kern = two ? (const void*)k_gemv_staged<2, BLOCK> : (const void*)k_gemv_staged<1, BLOCK>;
+        long long want = (a.n_rows + 31) / 32;
+        long long cap = (long long)ctx->sm_count * pk_blocks_per_sm(kern, BLOCK, smem);
+        if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
+        int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+        if (two) k_gemv_staged<2, BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
+        else k_gemv_staged<1, BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(a, ra);
+    } else {
+        long long want = ((a.n_rows + 3) / 4 + (BLOCK / 32) - 1) / (BLOCK / 32);      // a warp takes 4 rows at a time
+        long long cap = (long long)ctx->sm_count *
+                        pk_blocks_per_sm(two ? (const void*)k_gemv<2, BLOCK> : (const void*)k_gemv<1, BLOCK>, BLOCK, 0);
+        if (cap > ctx->red.max_blocks) cap = ctx->red.max_blocks;
+        int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+        if (two) k_gemv<2, BLOCK><<<grid, BLOCK, 0, ctx->stream>>>(a, ra);
+        else k_gemv<1, BLOCK><<<grid, BLOCK, 0, ctx->stream>>>(a, ra);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         pk_set_error("gemv launch: %s", cudaGetErrorString(e));
         return PK_ERR_CUDA;
     }
     ctx->launches++;
-    (void)m;
     return PK_OK;
 }
 

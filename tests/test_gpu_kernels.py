@@ -110,6 +110,25 @@ def test_dense_gemv(pk):
     np.testing.assert_allclose(y1.cpu().numpy(), a @ x1, rtol=1e-13, atol=1e-13)
 
 
+def test_dense_gemv_two_chains_staged_x_is_bitwise_the_single_chain_kernel(pk):
+    """Two right-hand sides on a wide dense block go through k_gemv_staged (x0 / x1 chunks staged in shared memory by
+    bulk copies); per row it adds in the order of the one-vector kernel, so both must agree bit for bit.  4610 columns =
+    two full chunks + a 514-column tail; 1003 rows = a ragged last row group."""
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((1003, 4610))
+    x0, x1 = rng.standard_normal(4610), rng.standard_normal(4610)
+    op = pk.Operator.from_dense_tensor(torch.from_numpy(a))
+    y0, y1 = op.matvec(torch.from_numpy(x0), x1=torch.from_numpy(x1))
+    s0 = op.matvec(torch.from_numpy(x0))
+    s1 = op.matvec(torch.from_numpy(x1))
+    assert torch.equal(y0, s0) and torch.equal(y1, s1)
+    ref = a.dot(x0)
+    np.testing.assert_allclose(y0.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    w = rng.standard_normal(1003)
+    _, sums = op.matvec(torch.from_numpy(x0), dot_with=torch.from_numpy(w))
+    np.testing.assert_allclose(sums.cpu().numpy(), [np.dot(w, ref), np.dot(ref, ref), np.dot(w, w)], rtol=1e-12)
+
+
 @pytest.mark.parametrize("mode,k", [(0, 0), (0, 1), (0, 4), (0, 8), (0, 12), (1, 0), (1, 2), (1, 4), (1, 8), (1, 16)])
 def test_gram_all_pairs(pk, mode, k):
     """The single-pass Gram kernel against the oracle's per-pair numpy.dot calls (kskipmrr.py:51-59, kskipcg.py:40-48)."""
