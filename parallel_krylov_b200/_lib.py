@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpkrylov.so")
+# PK_LIB: developer switch to load another build of the library (A/B experiments on kernel variants)
+LIB_PATH = os.environ.get("PK_LIB") or os.path.join(_HERE, "libpkrylov.so")
 
 PK_KMAX = 32
 PK_NCCL_ID_BYTES = 128

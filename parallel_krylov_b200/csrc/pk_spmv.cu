@@ -42,6 +42,7 @@ struct SpmvArgs {
     // (ranges 2 and 3), whose halo columns (>= n_own) are then read from this rank's receive buffer.
     const double* hrecv;          // this rank's receive buffer (nullptr: no exchange, columns index x directly)
     const PkHaloPush* hp;         // push descriptor in device memory
+    int halo_dry;                 // measurement aid (pk_ctx_set_nocomm): same kernel, but neither push nor flag waits
     long long n_own, n_halo;
     long long nnz_total;
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
@@ -190,16 +191,13 @@ struct TileMeta {
     int pad;
 };
 
-// Resident blocks per SM the fused-exchange (HALO) variants with 256-row tiles are compiled for: 4 for the single-vector
-// SpMV, 3 for the two-chain and fused-step forms — what their plain counterparts reach on their own — so that a rank of a
-// multi-GPU run streams A with as many bulk copies in flight as a single GPU does.  0 = no constraint (plain variants;
-// 128-row tiles are limited by shared memory).  NB: a constraint of 1 is NOT neutral — ptxas then spends 101 registers
-// on the plain SpMV, which halves its occupancy and costs 28 % of its bandwidth (measured, r02).
-template <int NV, int BLOCK, bool HALO, int FUSE>
-constexpr int spmv_min_blocks() { return (HALO && BLOCK == 256) ? ((NV == 1 && FUSE == 0) ? 4 : 3) : 0; }
-
+// NB on register budgets (tests/test_build_resources.py pins them): the plain single-vector variant needs 64 registers
+// = 4 resident blocks per SM.  The fused-exchange (HALO) variants reach the same budgets as their plain counterparts
+// because the push phase runs before anything else is live and the boundary tiles use a plain (not unrolled) row loop;
+// forcing them there with __launch_bounds__(256, 4) instead cost 30 % (spills + fewer gathers in flight), and a
+// constraint of 1 on the plain kernel made ptxas spend 101 registers and halve its occupancy (both measured, r02).
 template <int NV, int BLOCK, int STAGES, bool HALO, int FUSE>
-__global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>()) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
+__global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     if (pk_skip(ra)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[STAGES];
@@ -225,6 +223,64 @@ __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>(
             a.f_out = const_cast<double*>(t);
         }
         if (ra.dyn_last) a.reduce = (a.cj == kk) ? 1 : 0;
+    }
+    // ---- halo exchange, part 1: push (before anything else of the kernel is live in registers) ----------------------------
+    __shared__ int push_last;
+    if (HALO) {
+        const PkHaloPush* hp = a.hp;
+        // The first PK_PUSH_BLOCKS blocks push (a few thousand entries each: 2 x 2 MiB planes at 512^3 / 8 ranks); the
+        // others go straight to their tiles.  Every pushing block pays one system-scope fence before it may count
+        // itself done — with ALL ~600 blocks pushing, those fences alone cost ~250 us per SpMV (measured, r02).
+        const unsigned int n_push = gridDim.x < (unsigned)PK_PUSH_BLOCKS ? gridDim.x : (unsigned)PK_PUSH_BLOCKS;
+        if (blockIdx.x < n_push && !a.halo_dry) {
+            const unsigned long long hseq = *hp->seq + 1ull;
+            const int bank = (int)(hseq & 1ull);
+            const int P = hp->n_ranks;
+            const long long total = hp->send_off[P];
+            const long long stride = (long long)n_push * BLOCK;
+            constexpr int U = 4;                   // loads of U entries in flight before the remote stores
+            for (long long i0 = (long long)blockIdx.x * BLOCK + tid; i0 < total; i0 += U * stride) {
+                double v0[U], v1[U];
+                double* dst[U];
+                long long nh[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long i = i0 + u * stride;
+                    dst[u] = nullptr;
+                    if (i < total) {
+                        int q = 0;
+                        while (i >= hp->send_off[q + 1]) ++q;
+                        const long long kq = i - hp->send_off[q];
+                        const long long src = hp->send_contig[q] ? (long long)hp->send_first[q] + kq : (long long)hp->send_idx[i];
+                        nh[u] = hp->peer_nhalo[q];
+                        dst[u] = hp->peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh[u] + hp->dst_off[q] + kq;
+                        v0[u] = a.x0[src];
+                        if (NV == 2) v1[u] = a.x1[src];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (dst[u]) {
+                        dst[u][0] = v0[u];
+                        if (NV == 2) dst[u][nh[u]] = v1[u];
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                pk_fence_sys();          // release, cumulative over the block's remote stores (bar.sync above)
+                push_last = (atomicAdd(hp->ticket, 1u) == n_push - 1) ? 1 : 0;
+            }
+            __syncthreads();
+            if (push_last && tid < P && ((hp->peer_mask >> tid) & 1u)) {
+                // every pushing block's entries are on their way: raise this exchange's flag at every peer I talk to (also
+                // the ones that only send to me — the flag is their licence to reuse this bank two exchanges from now)
+                pk_fence_sys();
+                volatile unsigned long long* f =
+                    reinterpret_cast<volatile unsigned long long*>(hp->peer_recv[tid]) + bank * PK_MAX_RANKS + hp->me;
+                *f = hseq;
+            }
+        }
     }
     // tile index space: tiles of [row_lo,row_hi), then of [row_lo2,row_hi2), then of [row_lo3,row_hi3)
     const long long tiles_a = a.row_hi > a.row_lo ? (a.row_hi - a.row_lo + BLOCK - 1) / BLOCK : 0;
@@ -310,12 +366,11 @@ __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>(
     // this exchange = completed exchanges + 1 (the counter is advanced by the last block to LEAVE the kernel, so every
     // block reads the same value); its parity selects the bank of the peers' receive buffers.
     bool halo_ready = true;            // false until this block has seen the peers' flags of this exchange
-    __shared__ int push_last;
     // (the sequence number and the receive-buffer pointers are recomputed where they are needed instead of being kept
     // in registers across the tile loop: the interior tiles must not pay for the exchange)
     auto wait_halo = [&]() {           // all threads of the block
         const unsigned long long hseq = *a.hp->seq + 1ull;
-        if (tid < a.hp->n_ranks && ((a.hp->peer_mask >> tid) & 1u)) {
+        if (!a.halo_dry && tid < a.hp->n_ranks && ((a.hp->peer_mask >> tid) & 1u)) {
             const volatile unsigned long long* f =
                 reinterpret_cast<const volatile unsigned long long*>(a.hrecv) + (int)(hseq & 1ull) * PK_MAX_RANKS + tid;
             if (!pk_spin_until(f, hseq)) { ra.st->done = 1; ra.st->converged = 0; ra.st->guard = -2; }
@@ -324,63 +379,7 @@ __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>(
         __syncthreads();               // ... and, through the barrier, to the whole block
         halo_ready = true;
     };
-    if (HALO) {
-        const PkHaloPush* hp = a.hp;
-        // The first PK_PUSH_BLOCKS blocks push (a few thousand entries each: 2 x 2 MiB planes at 512^3 / 8 ranks); the
-        // others go straight to their tiles.  Every pushing block pays one system-scope fence before it may count
-        // itself done — with ALL ~600 blocks pushing, those fences alone cost ~250 us per SpMV (measured, r02).
-        const unsigned int n_push = gridDim.x < (unsigned)PK_PUSH_BLOCKS ? gridDim.x : (unsigned)PK_PUSH_BLOCKS;
-        if (blockIdx.x < n_push) {
-            const unsigned long long hseq = *hp->seq + 1ull;
-            const int bank = (int)(hseq & 1ull);
-            const int P = hp->n_ranks;
-            const long long total = hp->send_off[P];
-            const long long stride = (long long)n_push * BLOCK;
-            constexpr int U = 4;                   // loads of U entries in flight before the remote stores
-            for (long long i0 = (long long)blockIdx.x * BLOCK + tid; i0 < total; i0 += U * stride) {
-                double v0[U], v1[U];
-                double* dst[U];
-                long long nh[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const long long i = i0 + u * stride;
-                    dst[u] = nullptr;
-                    if (i < total) {
-                        int q = 0;
-                        while (i >= hp->send_off[q + 1]) ++q;
-                        const long long kq = i - hp->send_off[q];
-                        const long long src = hp->send_contig[q] ? (long long)hp->send_first[q] + kq : (long long)hp->send_idx[i];
-                        nh[u] = hp->peer_nhalo[q];
-                        dst[u] = hp->peer_recv[q] + PK_HALO_HDR + (size_t)(bank * 2) * nh[u] + hp->dst_off[q] + kq;
-                        v0[u] = a.x0[src];
-                        if (NV == 2) v1[u] = a.x1[src];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (dst[u]) {
-                        dst[u][0] = v0[u];
-                        if (NV == 2) dst[u][nh[u]] = v1[u];
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                pk_fence_sys();          // release, cumulative over the block's remote stores (bar.sync above)
-                push_last = (atomicAdd(hp->ticket, 1u) == n_push - 1) ? 1 : 0;
-            }
-            __syncthreads();
-            if (push_last && tid < P && ((hp->peer_mask >> tid) & 1u)) {
-                // every pushing block's entries are on their way: raise this exchange's flag at every peer I talk to (also
-                // the ones that only send to me — the flag is their licence to reuse this bank two exchanges from now)
-                pk_fence_sys();
-                volatile unsigned long long* f =
-                    reinterpret_cast<volatile unsigned long long*>(hp->peer_recv[tid]) + bank * PK_MAX_RANKS + hp->me;
-                *f = hseq;
-            }
-        }
-        halo_ready = false;
-    }
+    if (HALO) halo_ready = false;
     const int n_own = (int)a.n_own;
 
     // what a thread does with its finished row: store y (+ dots), or the fused k-skip step
@@ -435,29 +434,36 @@ __global__ void __launch_bounds__(BLOCK, spmv_min_blocks<NV, BLOCK, HALO, FUSE>(
                 const double fx = FUSE ? a.f_x[row] : 0.0;
                 const double xr = FUSE ? __ldg(a.x0 + row) : 0.0;
                 double sum0 = 0.0, sum1 = 0.0;
-                constexpr int UNR = 8;
-                for (int j = sb; j < se; j += UNR) {
-                    double vv[UNR], xa[UNR], xb[UNR];
+                if (!BND) {
+                    constexpr int UNR = 8;
+                    for (int j = sb; j < se; j += UNR) {
+                        double vv[UNR], xa[UNR], xb[UNR];
 #pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        const bool ok = j + u < se;
-                        const int c = ok ? scol[j + u] : 0;
-                        vv[u] = ok ? sval[j + u] : 0.0;
-                        if (!BND) {
+                        for (int u = 0; u < UNR; ++u) {
+                            const bool ok = j + u < se;
+                            const int c = ok ? scol[j + u] : 0;
+                            vv[u] = ok ? sval[j + u] : 0.0;
                             xa[u] = ok ? __ldg(a.x0 + c) : 0.0;
                             if (NV == 2) xb[u] = ok ? __ldg(a.x1 + c) : 0.0;
-                        } else {
-                            const bool own = c < n_own;
-                            xa[u] = ok ? (own ? __ldg(a.x0 + c) : __ldcg(h0 + c)) : 0.0;
-                            if (NV == 2) xb[u] = ok ? (own ? __ldg(a.x1 + c) : __ldcg(h1 + c)) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            if (j + u < se) {
+                                sum0 += vv[u] * xa[u];
+                                if (NV == 2) sum1 += vv[u] * xb[u];
+                            }
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        if (j + u < se) {
-                            sum0 += vv[u] * xa[u];
-                            if (NV == 2) sum1 += vv[u] * xb[u];
-                        }
+                } else {
+                    // boundary tiles are a few per cent of the tiles: a plain loop keeps the register footprint of the
+                    // fused-exchange variant at that of the plain kernel (the interior path above is what must be fast)
+#pragma unroll 1
+                    for (int j = sb; j < se; ++j) {
+                        const int c = scol[j];
+                        const double v = sval[j];
+                        const bool own = c < n_own;
+                        sum0 += v * (own ? __ldg(a.x0 + c) : __ldcg(h0 + c));
+                        if (NV == 2) sum1 += v * (own ? __ldg(a.x1 + c) : __ldcg(h1 + c));
                     }
                 }
                 finish_row(row, sum0, sum1, wi, fa, fb, fx, xr);
@@ -1307,7 +1313,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
     a.row_lo2 = a.row_hi2 = a.row_lo3 = a.row_hi3 = 0;
-    a.hrecv = nullptr; a.hp = nullptr; a.n_own = m->n_rows; a.n_halo = m->n_halo;
+    a.hrecv = nullptr; a.hp = nullptr; a.halo_dry = 0; a.n_own = m->n_rows; a.n_halo = m->n_halo;
     a.cap = m->tile_cap;
     {
         static int ef = -1;
@@ -1324,7 +1330,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     if (!exchange) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
-    } else if (m->halo_p2p && m->use_tma && !m->pat_on && !ctx->nocomm) {
+    } else if (m->halo_p2p && m->use_tma && !m->pat_on) {
         // Exchange fused into the operator kernel (ONE launch, no NCCL, no side stream): every block pushes its share of
         // my boundary entries into the peers' receive buffers over NVLink, the interior tiles run while the peers'
         // pushes are in flight, the boundary tiles (scheduled last) wait for the peers' flags in-kernel.
@@ -1333,6 +1339,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         a.row_lo3 = m->interior_hi; a.row_hi3 = m->n_rows;
         a.hrecv = m->d_recvbuf;
         a.hp = m->d_push;
+        a.halo_dry = ctx->nocomm ? 1 : 0;      // "compute only": the same kernel without push and waits (results meaningless)
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
     } else {
         // Interior rows (no halo column) run while the halo of x is in flight on the side stream; the boundary
