@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PK_VERSION 100
+#define PK_VERSION 101
 #define PK_KMAX 32            /* largest k of the k-skip solvers */
 #define PK_NCCL_ID_BYTES 128
 #define PK_IPC_HANDLE_BYTES 64
@@ -36,7 +36,9 @@ typedef enum {
     PK_MRR = 1,              /* v3/gpu/mrr.py:8           */
     PK_KSKIPCG = 2,          /* v3/gpu/kskipcg.py:9       */
     PK_KSKIPMRR = 3,         /* v3/gpu/kskipmrr.py:9      */
-    PK_ADAPTIVEKSKIPMRR = 4  /* v3/gpu/adaptivekskipmrr.py:10 (semantics of v3/cpu/adaptivekskipmrr.py) */
+    PK_ADAPTIVEKSKIPMRR = 4, /* v3/gpu/adaptivekskipmrr.py:10 (semantics of v3/cpu/adaptivekskipmrr.py) */
+    PK_CGCG = 5              /* Chronopoulos-Gear CG, one reduction per iteration, optional Jacobi preconditioner
+                                (v1/threads/pipeline/chronopoulos_gear.py:7) — opt-in, not a v3 method */
 } pk_method;
 
 typedef struct pk_ctx pk_ctx;   /* one per device/stream: scratch for reductions, SM count, optional communicator */
@@ -149,6 +151,7 @@ typedef struct {
     int32_t use_graph;     /* 1: replay a captured CUDA graph per batch; 0: plain stream launches                */
     int32_t x_is_zero;     /* 1: x0 == 0, skip the initial A·x (result identical: b - A·0 == b)                   */
     int64_t global_n;      /* global number of rows (== n_rows when not distributed)                             */
+    const double* d_mdiag; /* PK_CGCG only: diagonal of the Jacobi preconditioner M (local rows), u = r / M; NULL = none  */
 } pk_solve_opts;
 
 typedef struct {
@@ -161,6 +164,9 @@ typedef struct {
     int64_t kernel_launches; /* kernels this solve launched (bench.py's gpu_launches)                           */
     int64_t spmv_count;    /* operator applications                                                              */
 } pk_solve_result;
+
+/* d_out[i] = A[i][i] for the local rows (0 where the row stores no diagonal entry): the Jacobi preconditioner of PK_CGCG. */
+int pk_mat_diagonal(pk_mat* mat, double* d_out);
 
 /* Number of doubles of scratch (d_work) the solver needs for vectors of padded length `ld`. */
 int64_t pk_work_doubles(int method, int64_t ld, int k);

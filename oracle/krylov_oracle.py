@@ -335,7 +335,54 @@ def adaptivekskipmrr(mat, b, x=None, tol=1e-05, maxiter=None, k=0):
     return x, lg.info(idx, ok, khistory=khist[: idx + 1], final_k=k)
 
 
+def cgcg(mat, b, x=None, tol=1e-05, maxiter=None, M=None):
+    """Chronopoulos–Gear CG (one reduction point per iteration), optionally preconditioned —
+    /root/reference/v1/threads/pipeline/chronopoulos_gear.py:7-56, SURVEY.md §8f rank 4.
+
+    The reference file is a sketch that cannot be imported (``from .common import ...`` — there is no
+    ``pipeline/common.py``) and never updates ``old_gamma`` inside its loop (:30-31 vs :49), which makes ``beta`` wrong from
+    the second iteration on.  Restated here with those two repairs and nothing else changed in the arithmetic:
+    ``oracle/gen_golden_cgcg.py`` executes the reference text with exactly these repairs and pins this function on its
+    residual histories.  ``M``: None (u = r) or the 1-D diagonal of a Jacobi preconditioner (u = r / M; the reference's
+    ``ilu.solve(r)``, :25, :45).  v3 conventions for the interface: ``maxiter`` caps the number of solution updates,
+    ``nosl[i] = i`` for every recorded entry (the reference leaves the last entry unset when it breaks, :41-52)."""
+    lg = _Log(b, x, maxiter)
+    x = lg.x
+    minv = (lambda v: v.copy()) if M is None else (lambda v: v / M)
+    r = b - mat.dot(x)                        # :22
+    lg.res[0] = norm(r) / lg.bnorm            # :23
+    u = minv(r)                               # :25
+    w = mat.dot(u)                            # :26
+    alpha = dot(r, u) / dot(w, u)             # :28
+    beta = 0.0                                # :29
+    gamma = dot(r, u)                         # :30
+    p = np.zeros(lg.n, F64)                   # :33
+    s = np.zeros(lg.n, F64)                   # :34
+    it, ok = 0, False
+    lg.start()
+    while it < lg.maxiter:                    # :36
+        p = u + beta * p                      # :37
+        s = w + beta * s                      # :38
+        x += alpha * p                        # :39
+        r -= alpha * s                        # :40
+        it += 1
+        lg.nosl[it] = it
+        lg.res[it] = norm(r) / lg.bnorm       # :41
+        if lg.res[it] < tol:                  # :42
+            ok = True
+            break
+        u = minv(r)                           # :45
+        w = mat.dot(u)                        # :46
+        gamma_new = dot(r, u)                 # :47
+        delta = dot(w, u)                     # :48
+        beta = gamma_new / gamma              # :49 (with old_gamma kept up to date)
+        alpha = gamma_new / (delta - beta * gamma_new / alpha)   # :50
+        gamma = gamma_new
+    return x, lg.info(it, ok)
+
+
 SOLVERS = {
+    "cgcg": cgcg,
     "cg": cg,
     "mrr": mrr,
     "kskipcg": kskipcg,

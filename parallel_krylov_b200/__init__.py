@@ -10,6 +10,7 @@ from .mrr import mrr
 from .kskipcg import kskipcg
 from .kskipmrr import kskipmrr
 from .adaptivekskipmrr import adaptivekskipmrr
+from .cgcg import cgcg
 from ._core import Context, Operator, PkError
 
-__all__ = ["cg", "mrr", "kskipcg", "kskipmrr", "adaptivekskipmrr", "Context", "Operator", "PkError"]
+__all__ = ["cg", "mrr", "kskipcg", "kskipmrr", "adaptivekskipmrr", "cgcg", "Context", "Operator", "PkError"]

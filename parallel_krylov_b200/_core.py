@@ -342,7 +342,7 @@ def _banner_finish(elapsed, converged, iters, final_res, final_k=None):
 
 
 _NAMES = {"cg": "CG", "mrr": "MrR", "kskipcg": "k-skip CG", "kskipmrr": "k-skip MrR",
-          "adaptivekskipmrr": "Adaptive k-skip MrR"}
+          "adaptivekskipmrr": "Adaptive k-skip MrR", "cgcg": "chronopoulos gear"}
 
 
 def quiet() -> bool:
@@ -351,7 +351,7 @@ def quiet() -> bool:
 
 def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_every: int = 0,
           use_graph: Optional[bool] = None, verbose: Optional[bool] = None, ctx: Optional[Context] = None,
-          compress: Optional[bool] = None):
+          compress: Optional[bool] = None, M=None):
     """Shared body of the five entry points.  Returns ``(x, info)`` like the reference
     (/root/reference/v3/gpu/cg.py:47-52): x and the histories are torch CUDA tensors."""
     op = Operator.from_any(A, ctx)
@@ -401,9 +401,27 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
     nwork = int(lib.pk_work_doubles(mid, ld, k))
     work = torch.zeros(nwork, dtype=torch.float64, device=dev)
 
+    # Jacobi preconditioner of the Chronopoulos-Gear entry point: M = "jacobi" (diag(A), extracted on the device) or the
+    # diagonal itself (local rows).  The five v3 methods accept and ignore M like the reference (v3/cpu/cg.py:7).
+    mdiag = None
+    if method == "cgcg" and M is not None:
+        if isinstance(M, str):
+            if M != "jacobi":
+                raise PkError(f"unknown preconditioner {M!r} (None, 'jacobi' or the diagonal of M)")
+            mdiag = torch.empty(n, dtype=torch.float64, device=dev)
+            with torch.cuda.device(ctx.device):
+                check(lib.pk_mat_diagonal(op.handle, _ptr(mdiag)), "pk_mat_diagonal")
+        else:
+            mt = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float64)) if isinstance(M, np.ndarray) else M
+            if mt.numel() == op.n_global and op.n_global != n:
+                mt = mt[op.row0:op.row0 + n]
+            if mt.numel() != n:
+                raise PkError(f"M has {mt.numel()} entries; expected the diagonal for {n} local rows")
+            mdiag = mt.to(device=dev, dtype=torch.float64).contiguous()
     opts = SolveOpts(maxiter=maxiter, tol=float(tol), k=k, check_every=int(check_every),
                      use_graph=1 if (use_graph if use_graph is not None else True) else 0,
-                     x_is_zero=1 if x_is_zero else 0, global_n=op.n_global)
+                     x_is_zero=1 if x_is_zero else 0, global_n=op.n_global,
+                     d_mdiag=mdiag.data_ptr() if mdiag is not None else None)
     res = SolveResult()
     show = (not quiet()) if verbose is None else verbose
     if show and ctx.rank == 0:

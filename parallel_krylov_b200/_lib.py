@@ -15,14 +15,14 @@ LIB_PATH = os.environ.get("PK_LIB") or os.path.join(_HERE, "libpkrylov.so")
 PK_KMAX = 32
 PK_NCCL_ID_BYTES = 128
 PK_IPC_HANDLE_BYTES = 64
-PK_CG, PK_MRR, PK_KSKIPCG, PK_KSKIPMRR, PK_ADAPTIVEKSKIPMRR = range(5)
+PK_CG, PK_MRR, PK_KSKIPCG, PK_KSKIPMRR, PK_ADAPTIVEKSKIPMRR, PK_CGCG = range(6)
 METHOD_IDS = {"cg": PK_CG, "mrr": PK_MRR, "kskipcg": PK_KSKIPCG, "kskipmrr": PK_KSKIPMRR,
-              "adaptivekskipmrr": PK_ADAPTIVEKSKIPMRR}
+              "adaptivekskipmrr": PK_ADAPTIVEKSKIPMRR, "cgcg": PK_CGCG}
 
 
 class SolveOpts(C.Structure):
     _fields_ = [("maxiter", C.c_int64), ("tol", C.c_double), ("k", C.c_int32), ("check_every", C.c_int32),
-                ("use_graph", C.c_int32), ("x_is_zero", C.c_int32), ("global_n", C.c_int64)]
+                ("use_graph", C.c_int32), ("x_is_zero", C.c_int32), ("global_n", C.c_int64), ("d_mdiag", C.c_void_p)]
 
 
 class SolveResult(C.Structure):
@@ -65,6 +65,7 @@ _SIGS = {
     "pk_dot": (C.c_int, [_P, _I64, _P, _P, _P]),
     "pk_gram": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _P, C.c_int, _P]),
     "pk_work_doubles": (_I64, [C.c_int, _I64, C.c_int]),
+    "pk_mat_diagonal": (C.c_int, [_P, _P]),
     "pk_solve": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(SolveOpts),
                            C.POINTER(SolveResult)]),
     "pk_gen_stencil_counts": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P]),

@@ -89,6 +89,7 @@ struct PkRedArgs {
     int epi;                // PkEpi
     int defer;              // 1: only publish the sums (multi-GPU: all-reduce + pk_scalar_kernel follow)
     int g_off;              // >= 0: publish into st->gram[g_off + j] instead of st->red[j]
+    int red_off;            // publish into st->red[red_off + j] (local sums a LATER kernel all-reduces with its own)
     // split launches that feed ONE reduction (interior rows, then boundary rows after the halo arrived):
     int block_off;          // this launch's partials start at this block slot
     int nb_total;           // slots the final reduction covers (0: gridDim.x)
@@ -164,7 +165,7 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
         if (lane == 0) tot[j] = v;
     }
     __syncthreads();
-    double* dst = (ra.g_off >= 0) ? (ra.st->gram + ra.g_off) : ra.st->red;
+    double* dst = (ra.g_off >= 0) ? (ra.st->gram + ra.g_off) : (ra.st->red + ra.red_off);
     if (threadIdx.x == 0) {
         *ra.ticket = 0u;
         for (int j = 0; j < NS; ++j) dst[j] = tot[j];

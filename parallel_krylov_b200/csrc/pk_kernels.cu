@@ -182,6 +182,52 @@ __global__ void __launch_bounds__(EW_BLOCK) k_adapt_save(long long n, double* __
     else for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) best_x[i] = x[i];
 }
 
+// ---- Chronopoulos-Gear CG: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = r / M ;
+//      local sums {r.r, r.u} (all-reduced by the NEXT kernel, the SpMV w = A u, together with its u.w: ONE reduction
+//      point per iteration) — v1/threads/pipeline/chronopoulos_gear.py:37-47.  init: only u = r / M and the sums.
+//      Without a preconditioner u IS r (same buffer): the old r is read as u before it is overwritten.
+__global__ void __launch_bounds__(EW_BLOCK) k_cgcg_update(long long n, double* __restrict__ x, double* r, double* u,
+                                                          const double* __restrict__ w, double* __restrict__ p,
+                                                          double* __restrict__ s, const double* __restrict__ mdiag,
+                                                          int init, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    const double alpha = ra.st->alpha, beta = ra.st->beta;
+    double acc[2] = {0.0, 0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double ri = r[i];
+        if (!init) {
+            const double pi = u[i] + beta * p[i];
+            const double si = w[i] + beta * s[i];
+            p[i] = pi;
+            s[i] = si;
+            x[i] = x[i] + alpha * pi;
+            ri = ri - alpha * si;
+            r[i] = ri;
+        }
+        const double ui = mdiag ? ri / mdiag[i] : ri;
+        if (mdiag) u[i] = ui;
+        acc[0] += ri * ri;
+        acc[1] += ri * ui;
+    }
+    pk_grid_reduce<2, EW_BLOCK>(acc, ra);
+}
+
+__global__ void k_csr_diag(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                           const double* __restrict__ val, long long n_rows, double* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        double d = 0.0;
+        for (int q = rowptr[r]; q < rowptr[r + 1]; ++q)
+            if (col[q] == (int)r) d = val[q];
+        out[r] = d;
+    }
+}
+
+__global__ void k_dense_diag(const double* __restrict__ a, long long lda, long long n_rows, double* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
+        out[r] = a[r * lda + r];
+}
+
 // ---- k-skip CG step: x += a Ap0 ; Ar0 -= a Ap1 ; Ap0 = Ar0 + b Ap0 ; sums[0] = Ar0.Ar0  — kskipcg.py:53-55 -----
 __global__ void __launch_bounds__(EW_BLOCK) k_kscg_update(long long n, double* __restrict__ x,
                                                           double* __restrict__ ar0, const double* ap0, double* ap0_out,
@@ -356,6 +402,7 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
     ra.epi = epi;
     ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;
     ra.g_off = g_off;
+    ra.red_off = 0;
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
@@ -473,6 +520,31 @@ int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y,
     k_mrr_s<<<ew_grid(ctx, k_mrr_s, n), EW_BLOCK, 0, ctx->stream>>>(n, ar, y, r, red_args_n(ctx, EPI_MRR_ZETA, 2));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 2, EPI_MRR_ZETA, -1, 0);
+}
+
+int pk_launch_cgcg_update(pk_ctx* ctx, long long n, double* x, double* r, double* u, const double* w, double* p,
+                          double* s, const double* mdiag, int init) {
+    PkRedArgs ra = red_args(ctx, EPI_NONE);
+    ra.red_off = 3;          // local r.r / r.u wait in red[3..4] for the SpMV's all-reduce
+    ra.ar_n = 0;
+    ra.defer = 1;            // publish only: no epilogue here
+    ra.p2p = nullptr;
+    k_cgcg_update<<<ew_grid(ctx, k_cgcg_update, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, u, w, p, s, mdiag, init, ra);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+extern "C" int pk_mat_diagonal(pk_mat* m, double* d_out) {
+    PK_REQUIRE(m && d_out, "null argument");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    int grid = (int)((m->n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    if (grid < 1) grid = 1;
+    if (m->kind == MAT_DENSE) k_dense_diag<<<grid, 256, 0, ctx->stream>>>(m->dense, m->lda, m->n_rows, d_out);
+    else k_csr_diag<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, d_out);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
 }
 
 int pk_launch_adapt_save(pk_ctx* ctx, long long n, double* x, double* best_x) {

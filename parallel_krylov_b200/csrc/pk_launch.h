@@ -19,6 +19,8 @@ int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, d
 int pk_launch_mrr_s(pk_ctx* ctx, long long n, const double* ar, const double* y, const double* r);
 int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, double* z, const double* r,
                          double* r_out, double* r_alt, double* x, int cj, int epi);
+int pk_launch_cgcg_update(pk_ctx* ctx, long long n, double* x, double* r, double* u, const double* w, double* p,
+                          double* s, const double* mdiag, int init);
 int pk_launch_adapt_save(pk_ctx* ctx, long long n, double* x, double* best_x);
 int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, const double* ap0, double* ap0_out,
                           const double* ap1, int cj, int epi);
@@ -29,6 +31,7 @@ int pk_launch_gram(pk_ctx* ctx, int mode, long long n, long long ld, const doubl
 struct PkDots {
     const double* w = nullptr;   // sums: [0] = w.y, [1] = y.y, [2] = w.w   (nullptr: no reduction)
     int epi = EPI_NONE;
+    int extra_sums = 0;          // st->red[3 .. 3+extra) hold local sums of an EARLIER kernel: all-reduce them with these
     // k-skip step fused into the row epilogue (see SpmvArgs in pk_spmv.cu); only the TMA CSR kernel supports it
     int fuse = 0, cj = 0;
     double* f_a = nullptr;

@@ -336,6 +336,7 @@ extern "C" int64_t pk_work_doubles(int method, int64_t ld, int k) {
         case PK_KSKIPCG: nvec = (k + 1) + (k + 2) + 1; break;  // Ar[0..k], Ap[0..k+1], spare Ap0 (fused steps)
         case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 2; break;          // Ar[0..k+1], Ay[0..k], z, spare Ar0
         case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;  // + best_x
+        case PK_CGCG: nvec = 5; break;                     // r, w, p, s, u (u aliases r without a preconditioner)
         default: return -1;
     }
     return nvec * ld;
@@ -497,6 +498,32 @@ struct Solve {
             PK_CHECK(pk_launch_cg_xr(ctx, n, x, r, p, v));        // x += alpha p ; r -= alpha v ; gamma' ; beta ; test
             PK_CHECK(pk_launch_cg_p(ctx, n, p, r));               // p = r + beta p
             return PK_OK;
+        }));
+        return PK_OK;
+    }
+
+    // ---- Chronopoulos-Gear CG: /root/reference/v1/threads/pipeline/chronopoulos_gear.py:7-56 (with old_gamma kept up to
+    // date).  Two kernels and ONE reduction point per iteration: the fused update leaves its local r.r / r.u in
+    // PkState::red[3..4], the SpMV w = A u adds u.w and all-reduces the three together in its epilogue.
+    int cgcg() {
+        double *r = vec(0), *w = vec(1), *p = vec(2), *s = vec(3);
+        const double* md = o.d_mdiag;
+        double* u = md ? vec(4) : r;
+        PK_CHECK(initial_residual(r, nullptr, w, EPI_RES0));                       // :22-23
+        PK_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)ld * 2, ctx->stream));   // p, s (adjacent) = 0  :33-34
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        auto apply_u = [&](int epi) -> int {
+            PkDots d;
+            d.w = u;
+            d.epi = epi;
+            d.extra_sums = 2;
+            return pk_launch_spmv(ctx, A, u, w, nullptr, nullptr, d);
+        };
+        PK_CHECK(pk_launch_cgcg_update(ctx, n, x, r, u, w, p, s, md, 1));          // :25  u = M^-1 r ; r.u
+        PK_CHECK(apply_u(EPI_CGCG_INIT));                                          // :26-31
+        PK_CHECK(run_batches(1, 0, [&]() -> int {
+            PK_CHECK(pk_launch_cgcg_update(ctx, n, x, r, u, w, p, s, md, 0));      // :37-40, :45
+            return apply_u(EPI_CGCG);                                              // :46-50, :41-42
         }));
         return PK_OK;
     }
@@ -724,6 +751,7 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
         case PK_KSKIPCG: rc = s.kskipcg(); break;
         case PK_KSKIPMRR: rc = s.kskipmrr(); break;
         case PK_ADAPTIVEKSKIPMRR: rc = s.adaptive(); break;
+        case PK_CGCG: rc = s.cgcg(); break;
         default: pk_set_error("unknown method %d", method); return PK_ERR_ARG;
     }
     if (rc != PK_OK) {

@@ -1281,8 +1281,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.epi = dots.epi;
     ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;
     ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
-    ra.ar_n = dots.w ? 3 : ((dots.fuse && dots.epi != EPI_KS_STEP) ? 1 : 0);
+    ra.ar_n = dots.w ? 3 + dots.extra_sums : ((dots.fuse && dots.epi != EPI_KS_STEP) ? 1 : 0);
     ra.g_off = -1;
+    ra.red_off = 0;
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
@@ -1302,7 +1303,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         g.vec = (((uintptr_t)m->dense & 15) == 0 && (m->lda & 1) == 0 && ((uintptr_t)x & 15) == 0 &&
                  (!x1 || ((uintptr_t)x1 & 15) == 0)) ? 1 : 0;
         PK_CHECK(launch_gemv(ctx, m, two, g, ra));
-        if (dots.w) return pk_finish_reduce(ctx, 3, dots.epi, -1, 0);
+        if (dots.w) return pk_finish_reduce(ctx, 3 + dots.extra_sums, dots.epi, -1, 0);
         return PK_OK;
     }
 
@@ -1374,7 +1375,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         if (g_c > 0) PK_CHECK(launch_stream_any(ctx, m, two, ac, r3, &g_c, cap_each / 2, 2));
         if (!waited) PK_CHECK(pk_comm_halo_wait(ctx));
     }
-    if (dots.w) return pk_finish_reduce(ctx, 3, dots.epi, -1, 0);
+    if (dots.w) return pk_finish_reduce(ctx, 3 + dots.extra_sums, dots.epi, -1, 0);
     if (dots.fuse && dots.epi != EPI_KS_STEP) return pk_finish_reduce(ctx, 1, dots.epi, -1, 0);
     return PK_OK;
 }

@@ -67,6 +67,8 @@ enum PkEpi : int {
     EPI_ADAPT_FIRST,     // adaptive opening step: it = idx = 1 recorded (the loop-top logic is EPI_ADAPT_GUARD)
     EPI_ADAPT_TRIP_END,  // red[0] = r.r            -> it += k+1, idx++, res[idx], khist[idx]  (tested by the next guard)
     EPI_ADAPT_GUARD,     // (no sums) loop condition, residual-growth guard, convergence test at the top of a trip
+    EPI_CGCG_INIT,       // red[0] = u.w, red[3] = r.u          -> gamma, alpha = gamma/delta, beta = 0
+    EPI_CGCG,            // red[0] = u.w, red[3] = r.u, red[4] = r.r -> it++, res[it], stop test, beta, alpha (one reduction/iteration)
 };
 
 
@@ -214,6 +216,31 @@ PK_HD inline void pk_epilogue(int epi, PkState* st) {
                     st->done = 1;
                 }
             }
+            break;
+        }
+        case EPI_CGCG_INIT: {             // v1/threads/pipeline/chronopoulos_gear.py:28-31
+            st->gamma = s[3];
+            st->alpha = s[3] / s[0];
+            st->beta = 0.0;
+            break;
+        }
+        case EPI_CGCG: {                  // chronopoulos_gear.py:41-50 (old_gamma kept up to date), v3 stopping conventions
+            st->rr = s[4];
+            st->it += 1;
+            st->idx = st->it;
+            double res = sqrt(s[4]) / st->bnorm;
+            pk_record(st, st->it, st->it, res, false);
+            if (res < st->tol) {          // :42 — tested right after the update, before the loop condition
+                st->converged = 1;
+                st->done = 1;
+            } else if (!(st->it < st->maxiter)) {
+                st->converged = 0;
+                st->done = 1;
+            }
+            double g = s[3];
+            st->beta = g / st->gamma;                                   // :49
+            st->alpha = g / (s[0] - (st->beta * g) / st->alpha);        // :50
+            st->gamma = g;
             break;
         }
         case EPI_GRAM_CG:

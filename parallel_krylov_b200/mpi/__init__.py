@@ -4,7 +4,8 @@ from .mrr import mrr
 from .kskipcg import kskipcg
 from .kskipmrr import kskipmrr
 from .adaptivekskipmrr import adaptivekskipmrr
+from .cgcg import cgcg
 from ._dist import DistOperator, build_halo_plan, row_offsets_from_local
 
-__all__ = ["cg", "mrr", "kskipcg", "kskipmrr", "adaptivekskipmrr", "DistOperator", "build_halo_plan",
+__all__ = ["cg", "mrr", "kskipcg", "kskipmrr", "adaptivekskipmrr", "cgcg", "DistOperator", "build_halo_plan",
            "row_offsets_from_local"]

@@ -30,7 +30,8 @@ def main():
         "band27": problems.to_scipy(*problems.banded_spd(30011, 13, 0)),
         "dense": problems.dense_spd(384, 0),
     }
-    cases = [("cg", None), ("mrr", None), ("kskipcg", 2), ("kskipmrr", 2), ("kskipmrr", 4), ("adaptivekskipmrr", 4)]
+    cases = [("cg", None), ("mrr", None), ("kskipcg", 2), ("kskipmrr", 2), ("kskipmrr", 4), ("adaptivekskipmrr", 4),
+             ("cgcg", None)]
     for mname, A in mats.items():
         n = A.shape[0]
         base = n // world
@@ -59,6 +60,20 @@ def main():
                 assert info["converged"]
             except AssertionError as e:
                 failures.append(f"{tag} {e!r}"[:400])
+    # ---- Jacobi-preconditioned Chronopoulos-Gear CG (one all-reduce per iteration), diagonal extracted per rank
+    A = mats["band27"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
+    b = problems.rhs(n, "randn", 0)
+    xo, io = oracle.cgcg(A, b.copy(), tol=1e-8, M=A.diagonal().copy())
+    x, info = pkm.cgcg(None, A[lo:hi], b, tol=1e-8, M="jacobi")
+    res = info["residual"].cpu().numpy()
+    try:
+        assert abs(int(info["nosl"][-1]) - int(io["nosl"][-1])) <= 2
+        m = min(len(res), len(io["residual"]))
+        np.testing.assert_allclose(res[:m], io["residual"][:m], rtol=1e-10)
+        assert oracle.true_relres(A, b, x.cpu().numpy()) < 1e-8 * (1 + 1e-6)
+    except AssertionError as e:
+        failures.append(f"[cgcg jacobi rank {rank}] {e!r}"[:400])
+
     # ---- structurally nonsymmetric A (upper block triangular across the ranks): the last rank references no remote column
     # but its rows are needed by its predecessor -> a pure sender must still send / push, and must be throttled by its
     # receiver during the back-to-back basis SpMVs of the k-skip variants

@@ -212,3 +212,42 @@ def test_tiny_iteration_caps(pk, solver, k, cap):
     np.testing.assert_allclose(info["residual"].cpu().numpy(), io["residual"], rtol=1e-12)
     np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=1e-9, atol=1e-13)
     assert info["converged"] == io["converged"]
+
+
+# ---- Chronopoulos-Gear CG (opt-in) against the repaired reference text and the oracle ----------------
+import json as _json
+
+from parallel_krylov_b200 import problems
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cgcg_manifest.json")) as _fh:
+    _CGCG = _json.load(_fh)["cases"]
+
+
+@pytest.mark.parametrize("case", _CGCG, ids=[c["id"] for c in _CGCG])
+def test_cgcg_matches_reference_golden(pk, case):
+    kind, args = case["matrix"]
+    A = problems.to_scipy(*getattr(problems, kind)(*args))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case["id"] + ".npz")) as z:
+        gold = z["residual"]
+    M = "jacobi" if case["precond"] == "jacobi" else None
+    x, info = pk.cgcg(A, b, tol=1e-8, M=M)
+    res = info["residual"].cpu().numpy()
+    assert abs(int(info["nosl"][-1]) - case["iterations"]) <= 2
+    m = min(len(res), len(gold), 51)
+    np.testing.assert_allclose(res[:m], gold[:m], rtol=1e-10)
+    assert info["converged"]
+    assert oracle.true_relres(A, b, x.cpu().numpy()) < 1e-8 * (1 + 1e-6)
+    if M is not None:                      # the diagonal given explicitly is the same preconditioner
+        x2, info2 = pk.cgcg(A, b, tol=1e-8, M=A.diagonal().copy())
+        assert torch.equal(info2["residual"], info["residual"]) and torch.equal(x2, x)
+
+
+def test_cgcg_iteration_cap_and_plain_launches(pk):
+    A = problems.to_scipy(*problems.poisson2d(48))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    xo, io = oracle.cgcg(A, b.copy(), tol=1e-8, maxiter=17)
+    x, info = pk.cgcg(A, b, tol=1e-8, maxiter=17, use_graph=False)
+    assert int(info["nosl"][-1]) == int(io["nosl"][-1]) == 17 and not info["converged"]
+    np.testing.assert_allclose(info["residual"].cpu().numpy(), io["residual"], rtol=1e-10)
+    np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=1e-9, atol=1e-12)

@@ -3,6 +3,8 @@
 Runs on CPU (``-m "not gpu"``).  In the container that generated the goldens the match is bit for bit (same
 numpy/scipy/OpenBLAS calls in the same order); across machines OpenBLAS may split ``ddot`` differently, so the
 assertion is a tight relative tolerance for CG/MrR/small k and count-level for large k."""
+import os
+
 import numpy as np
 import pytest
 
@@ -63,3 +65,25 @@ def test_c_restatement_of_csr_matvec_matches_scipy_bitwise():
         r, c, v, n = hk.stencil_csr(*dims)
         hr, hc, hv, hn = problems.poisson3d(*dims) if dims[2] > 1 else problems._stencil_csr(dims[:2], 4.0)
         assert n == hn and np.array_equal(r, hr) and np.array_equal(c, hc) and np.array_equal(v, hv)
+
+
+# ---- Chronopoulos-Gear CG: the oracle against the repaired reference text ------------------------
+import json as _json
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cgcg_manifest.json")) as _fh:
+    CGCG_CASES = _json.load(_fh)["cases"]
+
+
+@pytest.mark.parametrize("case", CGCG_CASES, ids=[c["id"] for c in CGCG_CASES])
+def test_cgcg_oracle_reproduces_the_repaired_reference_bitwise(case):
+    from parallel_krylov_b200 import problems
+    kind, args = case["matrix"]
+    A = problems.to_scipy(*getattr(problems, kind)(*args))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    M = A.diagonal().copy() if case["precond"] == "jacobi" else None
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case["id"] + ".npz")) as z:
+        gold = z["residual"]
+    x, info = oracle.cgcg(A, b.copy(), tol=1e-8, M=M)
+    assert np.array_equal(info["residual"], gold)
+    assert info["converged"] and int(info["nosl"][-1]) == case["iterations"]
+    assert oracle.true_relres(A, b, x) < 1e-8 * (1 + 1e-6)
