@@ -7,7 +7,7 @@
  * Conventions: all pointers named d_* are DEVICE pointers (e.g. torch `tensor.data_ptr()`); buffers are
  * borrowed, never owned; every call is asynchronous on the context's stream unless stated; the return value is
  * 0 on success or a negative pk_status, with pk_last_error() giving the text.  No exceptions cross the ABI.
- * fp64 values, int32 CSR indices (nnz < 2^31 per rank — true for every BASELINE.json config).
+ * fp64 values, int32 column indices; row pointers int32 (pk_mat_csr) or int64 (pk_mat_csr64, nnz >= 2^31).
  */
 #ifndef PKRYLOV_H
 #define PKRYLOV_H
@@ -68,6 +68,12 @@ int pk_prof_end(pk_ctx* ctx, double* total_ms, int64_t* n_launches);
  * distributed: owned entries first, halo entries after, see pk_mat_set_halo).  Arrays are borrowed. */
 int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
                const int32_t* d_rowptr, const int32_t* d_col, const double* d_val);
+/* The same with 64-bit row pointers, for blocks of nnz >= 2^31 (column indices stay int32: fewer than 2^31 columns).
+ * The block is applied as row segments of < 2^31 nonzeros with 32-bit row pointers rebased per segment (built here, owned
+ * by the operator).  Single-GPU operators and distributed blocks that need no halo exchange; a distributed block that
+ * exchanges must have nnz < 2^31 (shard further). */
+int pk_mat_csr64(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
+                 const int64_t* d_rowptr, const int32_t* d_col, const double* d_val);
 /* Dense row-major block (the reference's np.ndarray branch, v3/gpu/common.py:100-101 → cuBLAS dgemv). */
 int pk_mat_dense(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols, const double* d_a, int64_t lda);
 int pk_mat_destroy(pk_mat* mat);
@@ -131,6 +137,12 @@ int pk_allgather(pk_ctx* ctx, const double* d_send, double* d_recv, int64_t n_pe
  * v3/gpu/cg.py:32, v3/gpu/mrr.py:41-42).  Distributed blocks exchange the halo of x first. */
 int pk_spmv(pk_ctx* ctx, pk_mat* mat, double* d_x, double* d_y, double* d_x1, double* d_y1,
             const double* d_w, double* d_sums);
+/* Matrix-powers kernel: levels l = 1..k of BOTH k-skip basis chains, (A^l u, A^l v), in ONE pass over A, written to
+ * d_base0 + l*ld and d_base1 + l*ld (ld = pk_mat_ld) from level 0 at d_base0 / d_base1 — bit-identical to k sequential
+ * pk_spmv calls.  Replaces the basis loops v3/cpu/kskipmrr.py:45-48, v3/cpu/kskipcg.py:36-39 for operators of small
+ * bandwidth (square single-GPU CSR block, rows of <= 28 nonzeros, half bandwidth bw with 640 - 2(k-1)bw >= 320);
+ * PK_ERR_UNSUPPORTED otherwise (the solvers then use k two-chain SpMV passes). */
+int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1);
 /* d_out[0] = u·v (local part; all-reduced when the context has a communicator). */
 int pk_dot(pk_ctx* ctx, int64_t n, const double* d_u, const double* d_v, double* d_out);
 /* All Gram sums of one k-skip outer trip in one pass (replaces the 6k+5 / 6k+7 cupy.dot calls,

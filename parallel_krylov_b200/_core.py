@@ -191,16 +191,23 @@ class Operator:
             return t.to(device=dev, dtype=dtype).contiguous()
         if int(n_cols) >= 2 ** 31:
             raise PkError("a block must have fewer than 2^31 columns (int32 column indices)")
-        rowptr, col, val = dv(rowptr, torch.int32), dv(col, torch.int32), dv(val, torch.float64)
+        # 64-bit row pointers (nnz >= 2^31): kept as int64, the library applies the block in row segments of < 2^31
+        # nonzeros (PK_SEG_NNZ forces that path with small segments: tests)
+        wide = rowptr.dtype == torch.int64 and rowptr.numel() > 0 and (
+            int(rowptr[-1]) >= 2 ** 31 or bool(os.environ.get("PK_SEG_NNZ")))
+        rowptr = dv(rowptr, torch.int64 if wide else torch.int32)
+        col, val = dv(col, torch.int32), dv(val, torch.float64)
         op.tensors = {"rowptr": rowptr, "col": col, "val": val}
         op.n_rows = rowptr.numel() - 1
         op.n_global = int(n_cols)
         op.nnz = int(val.numel())
         op.h2d_bytes = h2d
         op.kind = "csr"
+        op.index64 = wide
         with torch.cuda.device(ctx.device):
-            check(ctx.lib.pk_mat_csr(ctx.handle, C.byref(op.handle), op.n_rows, int(n_cols), op.nnz,
-                                     _ptr(rowptr), _ptr(col), _ptr(val)), "pk_mat_csr")
+            fn = ctx.lib.pk_mat_csr64 if wide else ctx.lib.pk_mat_csr
+            check(fn(ctx.handle, C.byref(op.handle), op.n_rows, int(n_cols), op.nnz, _ptr(rowptr), _ptr(col), _ptr(val)),
+                  "pk_mat_csr64" if wide else "pk_mat_csr")
         return op
 
     @classmethod
@@ -255,7 +262,7 @@ class Operator:
         Constant-coefficient stencils compress (27 patterns for the 3-D 7-point Laplacian); matrices with distinct
         values per row (e.g. ``problems.banded_spd``) do not and keep the CSR kernels.  The device verifies every row
         against its pattern before the switch."""
-        if self.kind != "csr" or self.n_rows == 0 or self.compressed:
+        if self.kind != "csr" or self.n_rows == 0 or self.compressed or getattr(self, "index64", False):
             return self.compressed
         ctx, dev, n = self.ctx, self.ctx.torch_device, self.n_rows
         rowptr, col, val = self.tensors["rowptr"], self.tensors["col"], self.tensors["val"]

@@ -43,6 +43,7 @@ _SIGS = {
     "pk_prof_begin": (C.c_int, [_P, C.c_int]),
     "pk_prof_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pk_mat_csr": (C.c_int, [_P, C.POINTER(_P), _I64, _I64, _I64, _P, _P, _P]),
+    "pk_mat_csr64": (C.c_int, [_P, C.POINTER(_P), _I64, _I64, _I64, _P, _P, _P]),
     "pk_mat_dense": (C.c_int, [_P, C.POINTER(_P), _I64, _I64, _P, _I64]),
     "pk_mat_destroy": (C.c_int, [_P]),
     "pk_mat_kernel_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -62,6 +63,7 @@ _SIGS = {
     "pk_allreduce_sum": (C.c_int, [_P, _P, _I64]),
     "pk_allgather": (C.c_int, [_P, _P, _P, _I64]),
     "pk_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "pk_matpow": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "pk_dot": (C.c_int, [_P, _I64, _P, _P, _P]),
     "pk_gram": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _P, C.c_int, _P]),
     "pk_work_doubles": (_I64, [C.c_int, _I64, C.c_int]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libpkrylov.so")
-SOURCES = ["pk_kernels.cu", "pk_spmv.cu", "pk_solvers.cu", "pk_comm.cu", "pk_generators.cu", "pk_persistent.cu"]
+SOURCES = ["pk_kernels.cu", "pk_spmv.cu", "pk_solvers.cu", "pk_comm.cu", "pk_generators.cu", "pk_persistent.cu", "pk_matpow.cu"]
 HEADERS = ["pk_common.cuh", "pk_device.cuh", "pk_scalars.h", "pk_state.h", "pk_launch.h", os.path.join(ROOT, "include", "pkrylov.h")]
 
 NVCC_FLAGS = [

@@ -112,11 +112,22 @@ struct PkHaloPush {
 
 enum PkMatKind : int { MAT_CSR_STREAM = 0, MAT_CSR_VECTOR = 1, MAT_DENSE = 2 };
 
+// A block with nnz >= 2^31 (64-bit row pointers from the caller) is applied as a few row SEGMENTS of < 2^31 nonzeros each:
+// per segment a 32-bit row pointer REBASED to the segment's first nonzero (owned by the operator), so the kernels keep
+// 32-bit offsets and stream 4 bytes of row pointer per row instead of 8.  Segments start at multiples of the tile height.
+struct PkSeg {
+    long long row_lo = 0, row_hi = 0;   // rows [row_lo, row_hi)
+    long long base = 0;                 // index of the segment's first nonzero in col / val
+    long long nnz = 0;
+    int32_t* rp32 = nullptr;            // owned: rp32[r - row_lo] = rowptr64[r] - base, r = row_lo .. row_hi
+};
+
 struct pk_mat {
     pk_ctx* ctx = nullptr;
     int kind = MAT_CSR_STREAM;
     long long n_rows = 0, n_cols = 0, nnz = 0;
-    const int32_t* rowptr = nullptr;
+    const int32_t* rowptr = nullptr;     // nullptr when the block is segmented (64-bit row pointers)
+    std::vector<PkSeg> segs;             // non-empty: apply segment by segment
     const int32_t* col = nullptr;
     const double* val = nullptr;
     const double* dense = nullptr;
@@ -146,6 +157,10 @@ struct pk_mat {
     // Row-pattern compression (opt-in, lossless): rows that share the same (column offsets relative to the row, values)
     // sequence are stored once in a small table; the matrix becomes one 16-bit pattern id per row.  Constant-coefficient
     // stencils have a few dozen patterns (27 for the 3-D 7-point Laplacian), so A shrinks from ~84 to 2 bytes per row.
+    // one-pass matrix-powers kernel (pk_matpow.cu): structure probe, cached
+    bool mp_checked = false;
+    int mp_rmax = 0;         // longest row
+    int mp_bw = 0;           // half bandwidth max |col - row|
     bool pat_on = false;
     int n_pat = 0, pat_entries = 0;
     const uint16_t* pat_id = nullptr;      // [n_rows]

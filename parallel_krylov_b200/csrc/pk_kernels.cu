@@ -207,18 +207,18 @@ __global__ void __launch_bounds__(EW_BLOCK) k_cgcg_update(long long n, double* _
         }
         const double ui = mdiag ? ri / mdiag[i] : ri;
         if (mdiag) u[i] = ui;
-        acc[0] += ri * ri;
-        acc[1] += ri * ui;
+        acc[0] += ri * ui;        // -> red[3] = r.u (gamma)
+        acc[1] += ri * ri;        // -> red[4] = r.r
     }
     pk_grid_reduce<2, EW_BLOCK>(acc, ra);
 }
 
 __global__ void k_csr_diag(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                           const double* __restrict__ val, long long n_rows, double* __restrict__ out) {
+                           const double* __restrict__ val, long long n_rows, long long row0, double* __restrict__ out) {
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
         double d = 0.0;
         for (int q = rowptr[r]; q < rowptr[r + 1]; ++q)
-            if (col[q] == (int)r) d = val[q];
+            if (col[q] == (int)(r + row0)) d = val[q];
         out[r] = d;
     }
 }
@@ -542,7 +542,11 @@ extern "C" int pk_mat_diagonal(pk_mat* m, double* d_out) {
     if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
     if (grid < 1) grid = 1;
     if (m->kind == MAT_DENSE) k_dense_diag<<<grid, 256, 0, ctx->stream>>>(m->dense, m->lda, m->n_rows, d_out);
-    else k_csr_diag<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, d_out);
+    else if (m->segs.empty()) k_csr_diag<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, 0, d_out);
+    else
+        for (const PkSeg& sg : m->segs)
+            k_csr_diag<<<grid, 256, 0, ctx->stream>>>(sg.rp32, m->col + sg.base, m->val + sg.base, sg.row_hi - sg.row_lo,
+                                                      sg.row_lo, d_out + sg.row_lo);
     PK_LAUNCH_CHECK();
     return PK_OK;
 }

@@ -43,7 +43,12 @@ bool pk_mat_can_fuse(const pk_mat* m);
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* mat, double* x, double* y, double* x1, double* y1, PkDots dots);
 int pk_csr_validate(pk_ctx* ctx, const void* rowptr, int rowptr64, const int32_t* col, long long n_rows,
                     long long n_cols, long long nnz, int* flags);
+int pk_rebase_rowptr(pk_ctx* ctx, const int64_t* rp64, long long base, long long count, int32_t* out);
 int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int tile_rows, int* result);
+
+// pk_matpow.cu — k levels of both basis chains in one pass over A (small-bandwidth operators)
+bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k);
+int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn);
 
 // pk_persistent.cu — whole CG loop as one cooperative kernel (small, L2-resident systems)
 int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double* p, double* v, int iters);

@@ -1,0 +1,218 @@
+// Matrix-powers kernel: the k-skip basis  A^l u, A^l v  (l = 1..k) of BOTH chains in ONE pass over A, for operators of
+// small bandwidth (every column within +-bw of its row; the banded system of BASELINE.json configs[3] has bw = 13).
+// Replaces the basis loops /root/reference/v3/cpu/kskipmrr.py:45-48 and kskipcg.py:36-39 (2k mat-vecs = 2k passes over
+// A in the reference, k two-chain passes in the SpMV path of this library).
+//
+// A block owns a window of T = 640 consecutive rows, one row per thread, and keeps its row of A — up to RMAX (value,
+// column offset) pairs — in REGISTERS for all k levels; the level vectors of the window ping-pong through shared memory.
+// Level l is only valid (l-1)*bw rows inside the window on either side (a trapezoid), so the block emits
+// T - 2(k-1)bw finished rows per window and neighbouring windows overlap by the ghost rows: A is re-read ~T/T_out times
+// (mostly from L2, the neighbour block just had it), instead of k times from HBM.  Per row the sum runs left to right
+// over the CSR entries with separately rounded products and sums, exactly like the SpMV kernels, so the basis is
+// bit-identical to k sequential operator applications (tests/test_gpu_kernels.py).
+#include "pk_device.cuh"
+#include "pk_launch.h"
+
+#include <stdlib.h>
+
+namespace {
+
+constexpr int MP_T = 640;       // rows per window = threads per block (one block per SM: the rows of A fill the registers)
+constexpr int MP_RMAX = 28;     // nonzeros per row kept in registers
+
+struct MpArgs {
+    const int32_t* rowptr;
+    const int32_t* col;
+    const double* val;
+    long long n;                // rows (square block, not distributed)
+    long long ld;               // distance between consecutive levels of a chain
+    double* base0;              // chain 0: level l at base0 + l * ld, l = 0 (input) .. k
+    double* base1;              // chain 1
+    int bw;                     // half bandwidth
+    int k;                      // levels to generate (dyn: the current k is read from PkState)
+    int dyn;
+};
+
+__global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    const int k = a.dyn ? ra.st->k : a.k;
+    if (k < 1) return;
+    const int bw = a.bw;
+    const int ghost = (k - 1) * bw;
+    const int t_out = MP_T - 2 * ghost;                 // finished rows per window (host guarantees >= MP_T / 2 for a.k)
+    const int W = MP_T + 2 * bw;                        // a level in shared memory: the window + bw entries on either side
+    extern __shared__ __align__(16) double mp_sm[];     // [chain 0..1][buffer 0..1][W]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * W; i += MP_T) mp_sm[i] = 0.0;     // pads of the buffers levels >= 1 are written into
+    __syncthreads();
+    const long long n_tiles = (a.n + t_out - 1) / t_out;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long o0 = tile * t_out;              // finished rows [o0, o1)
+        const long long o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
+        const long long s0 = o0 - ghost;                // first row of the window
+        const long long row = s0 + tid;
+        // ---- my row of A -> registers (column offsets relative to the row, packed 4 per register)
+        double v[MP_RMAX];
+        unsigned int offp[MP_RMAX / 4];
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < MP_RMAX / 4; ++t) offp[t] = 0u;
+#pragma unroll
+        for (int t = 0; t < MP_RMAX; ++t) v[t] = 0.0;
+        if (row >= 0 && row < a.n) {
+            const int q0 = __ldg(a.rowptr + row);
+            cnt = __ldg(a.rowptr + row + 1) - q0;
+#pragma unroll
+            for (int t = 0; t < MP_RMAX; ++t) {
+                if (t < cnt) {
+                    v[t] = __ldg(a.val + q0 + t);
+                    const int o = __ldg(a.col + q0 + t) - (int)row;
+                    offp[t >> 2] |= ((unsigned int)(o & 0xff)) << (8 * (t & 3));
+                }
+            }
+        }
+        // ---- level 0 of both chains -> shared memory (window + bw on either side; zeros outside the matrix)
+        double* P0 = mp_sm;
+        double* N0 = mp_sm + W;
+        double* P1 = mp_sm + 2 * W;
+        double* N1 = mp_sm + 3 * W;
+        for (int i = tid; i < W; i += MP_T) {
+            const long long g = s0 - bw + i;
+            const bool in = (g >= 0 && g < a.n);
+            P0[i] = in ? a.base0[g] : 0.0;
+            P1[i] = in ? a.base1[g] : 0.0;
+        }
+        __syncthreads();
+        for (int l = 1; l <= k; ++l) {
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < MP_RMAX; ++t) {
+                if (t < cnt) {                           // left to right over the CSR entries of the row
+                    const int o = (int)(signed char)((offp[t >> 2] >> (8 * (t & 3))) & 0xffu);
+                    const int idx = tid + bw + o;
+                    y0 += v[t] * P0[idx];
+                    y1 += v[t] * P1[idx];
+                }
+            }
+            N0[tid + bw] = y0;
+            N1[tid + bw] = y1;
+            if (row >= o0 && row < o1) {
+                a.base0[(size_t)l * a.ld + row] = y0;
+                a.base1[(size_t)l * a.ld + row] = y1;
+            }
+            __syncthreads();
+            double* t0 = P0; P0 = N0; N0 = t0;
+            double* t1 = P1; P1 = N1; N1 = t1;
+        }
+        // the buffer that held level 0 carried real neighbour data in its pads; levels >= 1 of the next window must not see
+        // stale pads of a different window as anything but finite numbers — they are finite, and only ever feed rows outside
+        // the valid trapezoid, so no reset is needed; the barrier above already separates this window from the next load.
+    }
+}
+
+__global__ void k_band_info(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, long long n_rows, int* out) {
+    int mlen = 0, mbw = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        const int q0 = rowptr[r], q1 = rowptr[r + 1];
+        mlen = (q1 - q0) > mlen ? (q1 - q0) : mlen;
+        if (q1 > q0) {        // sorted or not: look at both ends and, to be safe, every entry of short rows
+            for (int q = q0; q < q1 && q < q0 + 64; ++q) {
+                const long long d = (long long)col[q] - r;
+                const int ad = (int)(d < 0 ? -d : d) > (1 << 20) ? (1 << 20) : (int)(d < 0 ? -d : d);
+                mbw = ad > mbw ? ad : mbw;
+            }
+            if (q1 - q0 > 64) mbw = 1 << 20;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        int o = __shfl_down_sync(0xffffffffu, mlen, off);
+        mlen = o > mlen ? o : mlen;
+        o = __shfl_down_sync(0xffffffffu, mbw, off);
+        mbw = o > mbw ? o : mbw;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mlen);
+        atomicMax(out + 1, mbw);
+    }
+}
+
+}  // namespace
+
+// One-time (cached) structure probe: longest row and half bandwidth of a square, non-distributed CSR block.
+static int band_info(pk_ctx* ctx, pk_mat* m) {
+    if (m->mp_checked) return PK_OK;
+    m->mp_checked = true;
+    m->mp_rmax = 1 << 30;
+    m->mp_bw = 1 << 30;
+    if (m->kind == MAT_DENSE || m->distributed || !m->segs.empty() || m->rowptr == nullptr || m->n_rows != m->n_cols) return PK_OK;
+    int* d = nullptr;
+    int h[2] = {0, 0};
+    PK_CUDA(cudaMalloc(&d, 2 * sizeof(int)));
+    PK_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(int), ctx->stream));
+    int grid = (int)((m->n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_band_info<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->n_rows, d);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    m->mp_rmax = h[0];
+    m->mp_bw = h[1];
+    return PK_OK;
+}
+
+// Can the k levels of both chains be generated in one pass over A?  (small bandwidth, short rows, and the trapezoid must
+// keep at least half of the window: otherwise the two-chain SpMV passes are the better choice)
+bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PK_MATPOW");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || k < 2) return false;
+    if (band_info(ctx, m) != PK_OK) return false;
+    if (m->mp_rmax > MP_RMAX || m->mp_bw > 127 || m->mp_bw < 1) return false;
+    return MP_T - 2 * (k - 1) * m->mp_bw >= MP_T / 2;
+}
+
+int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn) {
+    MpArgs a;
+    a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
+    a.n = m->n_rows; a.ld = m->ld; a.base0 = base0; a.base1 = base1;
+    a.bw = m->mp_bw; a.k = k; a.dyn = dyn;
+    PkRedArgs ra{};
+    ra.st = ctx->d_state;
+    ra.only_rollback = ctx->ctl_only_rollback;
+    ra.dyn_cj = -1;
+    ra.dyn_last = 0;
+    const size_t smem = sizeof(double) * 4 * (size_t)(MP_T + 2 * a.bw);
+    pk_blocks_per_sm((const void*)k_matpow, MP_T, smem);          // opts in to the dynamic shared memory size if needed
+    const int t_out = MP_T - 2 * (k - 1) * a.bw;
+    long long n_tiles = (a.n + t_out - 1) / t_out;
+    int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+    if (grid < 1) grid = 1;
+    k_matpow<<<grid, MP_T, smem, ctx->stream>>>(a, ra);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pk_set_error("matrix-powers launch: %s", cudaGetErrorString(e));
+        return PK_ERR_CUDA;
+    }
+    ctx->launches++;
+    ctx->spmvs += 2LL * k;
+    return PK_OK;
+}
+
+// C-ABI building block (tests / benchmarks): levels 1..k of both chains from level 0 at d_base0 / d_base1.
+extern "C" int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1) {
+    PK_REQUIRE(ctx && mat && d_base0 && d_base1, "null argument");
+    PK_REQUIRE(k >= 1 && k <= PK_KMAX, "k out of range");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    if (!pk_matpow_ok(ctx, mat, k < 2 ? 2 : k)) {
+        pk_set_error("operator not eligible for the one-pass matrix-powers kernel (needs a square single-GPU CSR block, "
+                     "rows of <= %d nonzeros, half bandwidth bw with 640 - 2(k-1)bw >= 320; PK_MATPOW=0 disables it)", MP_RMAX);
+        return PK_ERR_UNSUPPORTED;
+    }
+    PK_CUDA(cudaMemsetAsync(&ctx->d_state->done, 0, sizeof(int), ctx->stream));
+    return pk_launch_matpow(ctx, mat, k, d_base0, d_base1, 0);
+}

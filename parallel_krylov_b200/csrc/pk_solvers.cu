@@ -153,42 +153,31 @@ extern "C" int pk_prof_end(pk_ctx* c, double* total_ms, int64_t* n_launches) {
 // ---------------------------------------------------------------------------------------------------------------
 static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
-extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
-                          const int32_t* d_rowptr, const int32_t* d_col, const double* d_val) {
-    PK_REQUIRE(ctx && out, "null argument");
-    PK_REQUIRE(n_rows >= 0 && nnz >= 0 && nnz < (1LL << 31), "CSR block must have 0 <= nnz < 2^31");
-    PK_REQUIRE(n_rows == 0 || (d_rowptr && (nnz == 0 || (d_col && d_val))), "null CSR arrays");
-    PK_REQUIRE(n_cols_local >= 0 && n_cols_local < (1LL << 31), "column space of a block must be < 2^31 (int32 indices)");
-    PK_CUDA(cudaSetDevice(ctx->device));
-    {
-        const char* e = getenv("PK_VALIDATE");        // PK_VALIDATE=0 skips the one-time structural check
-        if (n_rows > 0 && !(e && atoi(e) == 0)) {
-            int bad = 0;
-            PK_CHECK(pk_csr_validate(ctx, d_rowptr, 0, d_col, n_rows, n_cols_local, nnz, &bad));
-            if (bad) {
-                pk_set_error("malformed CSR block:%s%s%s%s", (bad & 1) ? " rowptr[0] != 0;" : "",
-                             (bad & 2) ? " rowptr not monotone;" : "", (bad & 4) ? " rowptr[n_rows] != nnz;" : "",
-                             (bad & 8) ? " column index outside [0, n_cols);" : "");
-                return PK_ERR_ARG;
-            }
-        }
+static int csr_check(pk_ctx* ctx, const void* rowptr, int rowptr64, const int32_t* col, long long n_rows,
+                     long long n_cols, long long nnz) {
+    const char* e = getenv("PK_VALIDATE");        // PK_VALIDATE=0 skips the one-time structural check
+    if (n_rows <= 0 || (e && atoi(e) == 0)) return PK_OK;
+    int bad = 0;
+    PK_CHECK(pk_csr_validate(ctx, rowptr, rowptr64, col, n_rows, n_cols, nnz, &bad));
+    if (bad) {
+        pk_set_error("malformed CSR block:%s%s%s%s", (bad & 1) ? " rowptr[0] != 0;" : "",
+                     (bad & 2) ? " rowptr not monotone;" : "", (bad & 4) ? " rowptr[n_rows] != nnz;" : "",
+                     (bad & 8) ? " column index outside [0, n_cols);" : "");
+        return PK_ERR_ARG;
     }
-    pk_mat* m = new pk_mat();
-    m->ctx = ctx;
-    m->n_rows = n_rows;
-    m->n_cols = n_cols_local;
-    m->nnz = nnz;
-    m->rowptr = d_rowptr;
-    m->col = d_col;
-    m->val = d_val;
-    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0) && (((uintptr_t)d_rowptr & 15) == 0);
-    // Kernel choice from the nnz distribution (mean row length): tiles of 256 rows (128 for mid-length rows) staged in
-    // shared memory when a tile's nonzeros fit; otherwise the warp-per-row path handles the tile.
+    return PK_OK;
+}
+
+// Kernel choice from the nnz distribution (mean row length): tiles of 256 rows (128 for mid-length rows) staged in
+// shared memory when a tile's nonzeros fit; otherwise the warp-per-row path handles the tile.
+static int csr_tile_rows(long long n_rows, long long nnz) {
     const double mean = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
-    m->tile_rows = mean <= 12.0 ? 256 : 128;
+    return mean <= 12.0 ? 256 : 128;
+}
+
+static void csr_choose_kernel(pk_mat* m, int tile_max) {
+    const double mean = m->n_rows > 0 ? (double)m->nnz / (double)m->n_rows : 0.0;
     long long heur = (long long)(m->tile_rows * mean * 1.25) + 64;      // room for moderately irregular rows
-    int tile_max = 0;
-    if (n_rows > 0) PK_CHECK(pk_tile_max_nnz(ctx, d_rowptr, n_rows, m->tile_rows, &tile_max));
     long long cap = std::min<long long>(heur, (long long)tile_max + 3);  // +3: the staged window starts 16-byte aligned
     cap = std::max<long long>(round_up(cap, 64), 256);
     if (mean <= 40.0 && cap * 12 <= 96 * 1024) {
@@ -198,14 +187,123 @@ extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_c
         m->tile_cap = 256;        // practically every tile exceeds this: rows are reduced warp-per-row
         m->kind = MAT_CSR_VECTOR;
     }
-    {
-        const char* e = getenv("PK_SPMV");            // "stream": plain-load kernel; default: TMA-pipelined kernel
-        m->use_tma = m->vec_ok && !(e && strcmp(e, "stream") == 0);
-        const char* st = getenv("PK_SPMV_STAGES");
-        m->stages = st ? atoi(st) : 2;
-        if (m->stages < 2 || m->stages > 4) m->stages = 2;
+    const char* e = getenv("PK_SPMV");            // "stream": plain-load kernel; default: TMA-pipelined kernel
+    m->use_tma = m->vec_ok && !(e && strcmp(e, "stream") == 0);
+    const char* st = getenv("PK_SPMV_STAGES");
+    m->stages = st ? atoi(st) : 2;
+    if (m->stages < 2 || m->stages > 4) m->stages = 2;
+    m->ld = round_up(std::max<long long>(m->n_rows, m->n_cols), 32);
+}
+
+extern "C" int pk_mat_csr(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
+                          const int32_t* d_rowptr, const int32_t* d_col, const double* d_val) {
+    PK_REQUIRE(ctx && out, "null argument");
+    PK_REQUIRE(n_rows >= 0 && nnz >= 0 && nnz < (1LL << 31), "pk_mat_csr takes 0 <= nnz < 2^31 (use pk_mat_csr64 beyond)");
+    PK_REQUIRE(n_rows == 0 || (d_rowptr && (nnz == 0 || (d_col && d_val))), "null CSR arrays");
+    PK_REQUIRE(n_cols_local >= 0 && n_cols_local < (1LL << 31), "column space of a block must be < 2^31 (int32 indices)");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(csr_check(ctx, d_rowptr, 0, d_col, n_rows, n_cols_local, nnz));
+    pk_mat* m = new pk_mat();
+    m->ctx = ctx;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols_local;
+    m->nnz = nnz;
+    m->rowptr = d_rowptr;
+    m->col = d_col;
+    m->val = d_val;
+    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0) && (((uintptr_t)d_rowptr & 15) == 0);
+    m->tile_rows = csr_tile_rows(n_rows, nnz);
+    int tile_max = 0;
+    if (n_rows > 0) {
+        int rc = pk_tile_max_nnz(ctx, d_rowptr, n_rows, m->tile_rows, &tile_max);
+        if (rc != PK_OK) { delete m; return rc; }
     }
-    m->ld = round_up(std::max<long long>(n_rows, n_cols_local), 32);
+    csr_choose_kernel(m, tile_max);
+    *out = m;
+    return PK_OK;
+}
+
+static void free_segs(pk_mat* m) {
+    for (PkSeg& sg : m->segs)
+        if (sg.rp32) cudaFree(sg.rp32);
+    m->segs.clear();
+}
+
+extern "C" int pk_mat_csr64(pk_ctx* ctx, pk_mat** out, int64_t n_rows, int64_t n_cols_local, int64_t nnz,
+                            const int64_t* d_rowptr, const int32_t* d_col, const double* d_val) {
+    PK_REQUIRE(ctx && out, "null argument");
+    PK_REQUIRE(n_rows >= 0 && nnz >= 0, "negative size");
+    PK_REQUIRE(n_rows == 0 || (d_rowptr && (nnz == 0 || (d_col && d_val))), "null CSR arrays");
+    PK_REQUIRE(n_cols_local >= 0 && n_cols_local < (1LL << 31), "column space of a block must be < 2^31 (int32 indices)");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(csr_check(ctx, d_rowptr, 1, d_col, n_rows, n_cols_local, nnz));
+    pk_mat* m = new pk_mat();
+    m->ctx = ctx;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols_local;
+    m->nnz = nnz;
+    m->col = d_col;
+    m->val = d_val;
+    m->vec_ok = (((uintptr_t)d_col & 15) == 0) && (((uintptr_t)d_val & 15) == 0);
+    m->tile_rows = csr_tile_rows(n_rows, nnz);
+    // segment size: below 2^31 with room for rounding the cut to a tile boundary (PK_SEG_NNZ: tests use tiny segments)
+    long long seg_max = (1LL << 31) - (1LL << 24);
+    if (const char* e = getenv("PK_SEG_NNZ")) seg_max = std::max<long long>(atoll(e), 64);
+    const long long n_seg = std::max<long long>(1, (nnz + seg_max - 1) / seg_max);
+    auto rp_at = [&](long long r, long long* v) -> int {      // one 8-byte D2H read (a handful per cut)
+        PK_CUDA(cudaMemcpyAsync(v, d_rowptr + r, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return PK_OK;
+    };
+    std::vector<long long> cuts{0};
+    for (long long sgi = 1; sgi < n_seg; ++sgi) {
+        const long long target = (long long)((double)nnz * (double)sgi / (double)n_seg);
+        long long lo = cuts.back(), hi = n_rows;              // first row r with rowptr[r] >= target
+        while (lo < hi) {
+            const long long mid = (lo + hi) / 2;
+            long long v = 0;
+            int rc = rp_at(mid, &v);
+            if (rc != PK_OK) { delete m; return rc; }
+            if (v < target) lo = mid + 1; else hi = mid;
+        }
+        const long long cut = lo / m->tile_rows * m->tile_rows;   // tile boundary (keeps the staged windows 16-byte aligned)
+        if (cut > cuts.back() && cut < n_rows) cuts.push_back(cut);
+    }
+    cuts.push_back(n_rows);
+    int tile_max = 0;
+    for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+        PkSeg sg;
+        sg.row_lo = cuts[i];
+        sg.row_hi = cuts[i + 1];
+        long long b0 = 0, b1 = 0;
+        int rc = rp_at(sg.row_lo, &b0);
+        if (rc == PK_OK) rc = rp_at(sg.row_hi, &b1);
+        if (rc == PK_OK && b1 - b0 >= (1LL << 31)) {
+            pk_set_error("rows %lld..%lld hold %lld nonzeros: a segment of < 2^31 cannot be cut at a tile boundary",
+                         sg.row_lo, sg.row_hi, b1 - b0);
+            rc = PK_ERR_UNSUPPORTED;
+        }
+        if (rc == PK_OK && cudaMalloc(&sg.rp32, sizeof(int32_t) * (size_t)(sg.row_hi - sg.row_lo + 4)) != cudaSuccess) {
+            pk_set_error("cudaMalloc of a segment row pointer failed");
+            rc = PK_ERR_CUDA;
+        }
+        if (rc == PK_OK) {
+            sg.base = b0;
+            sg.nnz = b1 - b0;
+            rc = pk_rebase_rowptr(ctx, d_rowptr + sg.row_lo, b0, sg.row_hi - sg.row_lo + 1, sg.rp32);
+        }
+        int tmax = 0;
+        if (rc == PK_OK && sg.row_hi > sg.row_lo) rc = pk_tile_max_nnz(ctx, sg.rp32, sg.row_hi - sg.row_lo, m->tile_rows, &tmax);
+        if (rc != PK_OK) {
+            if (sg.rp32) cudaFree(sg.rp32);
+            free_segs(m);
+            delete m;
+            return rc;
+        }
+        tile_max = std::max(tile_max, tmax);
+        m->segs.push_back(sg);
+    }
+    csr_choose_kernel(m, tile_max);
     *out = m;
     return PK_OK;
 }
@@ -230,6 +328,7 @@ extern "C" int pk_mat_destroy(pk_mat* m) {
     if (!m) return PK_OK;
     if (m->d_sendbuf) cudaFree(m->d_sendbuf);
     pk_mat_halo_p2p_close(m);
+    free_segs(m);
     delete m;
     return PK_OK;
 }
@@ -255,6 +354,8 @@ extern "C" int pk_mat_set_halo(pk_mat* m, int n_peers_total, const int64_t* send
                                int64_t interior_hi) {
     PK_REQUIRE(m && send_off && recv_off, "null argument");
     PK_REQUIRE(n_peers_total == m->ctx->n_ranks, "halo plan size != communicator size");
+    PK_REQUIRE(m->segs.empty() || (recv_off[n_peers_total] == 0 && send_off[n_peers_total] == 0),
+               "a distributed block that exchanges a halo must have nnz < 2^31 (shard it over more ranks)");
     const int P = n_peers_total;
     m->send_off.assign(send_off, send_off + P + 1);
     m->recv_off.assign(recv_off, recv_off + P + 1);
@@ -532,7 +633,7 @@ struct Solve {
     bool use_persistent() const {
         const char* e = getenv("PK_PERSISTENT");                   // 0: never, 1: whenever possible, unset: by size
         const int mode = e ? atoi(e) : -1;
-        if (mode == 0 || ctx->n_ranks > 1 || A->kind == MAT_DENSE || A->distributed) return false;
+        if (mode == 0 || ctx->n_ranks > 1 || A->kind == MAT_DENSE || A->distributed || !A->segs.empty()) return false;
         if (mode == 1) return true;
         // measured on B200 (graph replay vs persistent): 2-D 256^2 (65 k rows) 62.7 k -> 109 k it/s; 128^3 (2.1 M rows)
         // 15.5 k vs 12.5 k it/s.  Below ~300 k rows the launches dominate, above the TMA-pipelined kernels win.
@@ -562,12 +663,15 @@ struct Solve {
         auto Ap = [&](int j) { return vec(k + 1 + j); };          // rows 0..k+1
         double* spare = vec(2 * k + 3);                           // second home of Ap[0] for the fused steps
         const bool fuse = pk_mat_can_fuse(A);
+        const bool mp = pk_matpow_ok(ctx, A, k);
         PK_CHECK(initial_residual(Ar(0), Ap(0), Ap(1), EPI_CG_INIT));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         PK_CHECK(apply(Ap(0), Ap(1)));                            // invariant: Ap[1] = A Ap[0] at trip start
         PK_CHECK(run_batches(k + 1, 0, [&]() -> int {
-            // basis: one pass over A advances both chains: (Ar[j], Ap[j+1]) = A (Ar[j-1], Ap[j])
-            for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j - 1), Ar(j), Ap(j), Ap(j + 1)));
+            // basis: (Ar[j], Ap[j+1]) = A (Ar[j-1], Ap[j]), j = 1..k — all k levels of both chains in ONE pass over A when
+            // the operator's bandwidth allows (pk_matpow.cu), else one pass over A per level
+            if (mp) PK_CHECK(pk_launch_matpow(ctx, A, k, Ar(0), Ap(1), 0));
+            else for (int j = 1; j <= k; ++j) PK_CHECK(apply2(Ar(j - 1), Ar(j), Ap(j), Ap(j + 1)));
             PK_CHECK(pk_launch_gram(ctx, 1, n, ld, Ar(0), k + 1, Ap(0), k + 2, k + 2, EPI_GRAM_CG));
             if (!fuse) {
                 for (int j = 0; j <= k; ++j) {
@@ -626,9 +730,14 @@ struct Solve {
         double* z = vec(2 * k_alloc + 3);
         double* spare = vec(2 * k_alloc + 4);                     // second home of Ar[0] for the fused steps
         const int end_epi = dyn ? EPI_ADAPT_TRIP_END : EPI_KS_TRIP_END;
-        for (int j = 1; j <= k; ++j) {
-            Ctl c(ctx, 0, dyn ? j : -1, 0);
-            PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
+        if (pk_matpow_ok(ctx, A, k)) {
+            // all k levels of both chains in ONE pass over A (pk_matpow.cu); dyn: the kernel reads the current k itself
+            PK_CHECK(pk_launch_matpow(ctx, A, k, Ar(1), Ay(0), dyn ? 1 : 0));
+        } else {
+            for (int j = 1; j <= k; ++j) {
+                Ctl c(ctx, 0, dyn ? j : -1, 0);
+                PK_CHECK(apply2(Ar(j), Ar(j + 1), Ay(j - 1), Ay(j)));
+            }
         }
         {
             Ctl c(ctx, 0, dyn ? 0 : -1, 0);

@@ -46,6 +46,8 @@ struct SpmvArgs {
     long long n_own, n_halo;
     long long nnz_total;
     long long rowptr_len;   // entries of rowptr (n_rows_total + 1)
+    int base_mis;           // (index of col[0]/val[0] in the caller's arrays) mod 4: a row segment of a block with 64-bit
+                            // row pointers starts anywhere, and the staged windows must start 16-byte aligned in MEMORY
     int cap;                // staging capacity (nonzeros) per right-hand side
     int evict_first;        // CSR arrays are streamed with an L2 evict-first hint (keeps the vectors in L2)
     int blocked;            // tile -> block assignment: 1 contiguous chunks per block, 0 grid-strided
@@ -79,13 +81,13 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra)
         for (int t = tid; t <= nr; t += BLOCK) rp[t] = a.rowptr[r0 + t];
         __syncthreads();
         const int base = rp[0], end = rp[nr];
-        const int q0 = VEC ? (base & ~3) : base;                     // 16-byte aligned start of the staged window
+        const int q0 = VEC ? (((base + a.base_mis) & ~3) - a.base_mis) : base;   // 16-byte aligned start of the staged window
         if (end - q0 <= a.cap) {
             // ---- phase 1: stream the tile's (col, val) into shared memory, 128-bit coalesced ------------------
             if (VEC) {
                 for (int q = q0 + 4 * tid; q < end; q += 4 * BLOCK) {
                     const int i = q - q0;
-                    if ((long long)q + 4 <= a.nnz_total) {
+                    if (q >= 0 && (long long)q + 4 <= a.nnz_total) {
                         const int4 c4 = __ldg(reinterpret_cast<const int4*>(a.col + q));
                         const double2 v01 = __ldg(reinterpret_cast<const double2*>(a.val + q));
                         const double2 v23 = __ldg(reinterpret_cast<const double2*>(a.val + q + 2));
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_stream(SpmvArgs a, PkRedArgs ra)
                         *reinterpret_cast<double2*>(sval + i + 2) = v23;
                     } else {
                         for (int e = 0; e < 4 && (long long)q + e < a.nnz_total; ++e) {
+                            if (q + e < 0) continue;          // entries before the segment: never referenced by a row
                             scol[i + e] = a.col[q + e];
                             sval[i + e] = a.val[q + e];
                         }
@@ -317,11 +320,11 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
         long long r0, rend;
         tile_rows(tile, r0, rend);
         const int nr = (int)((rend - r0) < BLOCK ? (rend - r0) : BLOCK);
-        const int q0 = nb & ~3;
+        const int q0 = ((nb + a.base_mis) & ~3) - a.base_mis;     // aligned in memory; may be -1..-3 at a segment start
         const int cnt = (ne - q0 + 3) & ~3;
         const long long ra0 = r0 & ~3LL;
         const int rcnt = (int)((r0 - ra0) + nr + 1 + 3) & ~3;
-        const bool ok = cnt <= a.cap && (long long)q0 + cnt <= a.nnz_total && ra0 + rcnt <= a.rowptr_len;
+        const bool ok = q0 >= 0 && cnt <= a.cap && (long long)q0 + cnt <= a.nnz_total && ra0 + rcnt <= a.rowptr_len;
         meta[s].q0 = q0;
         meta[s].ra0 = (int)(r0 - ra0);
         meta[s].bulk = ok ? 1 : 0;
@@ -1162,6 +1165,20 @@ __global__ void k_csr_validate(const RP* __restrict__ rowptr, const int32_t* __r
 
 }  // namespace
 
+__global__ void k_rebase_rowptr(const long long* __restrict__ rp64, long long base, long long count, int32_t* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (int32_t)(rp64[i] - base);
+}
+
+int pk_rebase_rowptr(pk_ctx* ctx, const int64_t* rp64, long long base, long long count, int32_t* out) {
+    int grid = (int)((count + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_rebase_rowptr<<<grid, 256, 0, ctx->stream>>>((const long long*)rp64, base, count, out);
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
 int pk_csr_validate(pk_ctx* ctx, const void* rowptr, int rowptr64, const int32_t* col, long long n_rows,
                     long long n_cols, long long nnz, int* flags) {
     int* d = nullptr;
@@ -1204,7 +1221,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
 // ---- row-pattern compression: C-ABI ---------------------------------------------------------------------------------
 extern "C" int pk_mat_row_hashes(pk_mat* m, uint64_t* d_hash) {
     PK_REQUIRE(m && d_hash, "null argument");
-    PK_REQUIRE(m->kind != MAT_DENSE, "row patterns apply to CSR blocks");
+    PK_REQUIRE(m->kind != MAT_DENSE && m->segs.empty(), "row patterns apply to CSR blocks with 32-bit row pointers");
     pk_ctx* ctx = m->ctx;
     PK_CUDA(cudaSetDevice(ctx->device));
     int grid = (int)((m->n_rows + 255) / 256);
@@ -1218,7 +1235,7 @@ extern "C" int pk_mat_row_hashes(pk_mat* m, uint64_t* d_hash) {
 extern "C" int pk_mat_set_patterns(pk_mat* m, int n_pat, int n_entries, const uint16_t* d_id, const int32_t* d_ptr,
                                    const int32_t* d_off, const double* d_val) {
     PK_REQUIRE(m && d_id && d_ptr && d_off && d_val, "null argument");
-    PK_REQUIRE(m->kind != MAT_DENSE, "row patterns apply to CSR blocks");
+    PK_REQUIRE(m->kind != MAT_DENSE && m->segs.empty(), "row patterns apply to CSR blocks with 32-bit row pointers");
     PK_REQUIRE(n_pat >= 1 && n_pat <= 65535 && n_entries >= 0 && (size_t)n_entries * 12 + (size_t)(n_pat + 1) * 4 <= 64 * 1024,
                "pattern table too large for shared memory");
     pk_ctx* ctx = m->ctx;
@@ -1313,6 +1330,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.fuse = dots.fuse; a.cj = dots.cj; a.f_a = dots.f_a; a.f_b = dots.f_b; a.f_x = dots.f_x; a.f_out = dots.f_out;
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
+    a.base_mis = 0;
     a.row_lo2 = a.row_hi2 = a.row_lo3 = a.row_hi3 = 0;
     a.hrecv = nullptr; a.hp = nullptr; a.halo_dry = 0; a.n_own = m->n_rows; a.n_halo = m->n_halo;
     a.cap = m->tile_cap;
@@ -1328,7 +1346,36 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     int grid = 0;
 
     const bool exchange = m->distributed && (m->n_halo > 0 || (!m->send_off.empty() && m->send_off.back() > 0));
-    if (!exchange) {
+    if (!exchange && !m->segs.empty()) {
+        // block with 64-bit row pointers: one launch per row segment (< 2^31 nonzeros each, 32-bit row pointer rebased to
+        // the segment), all feeding ONE reduction through disjoint block slots like the interior / boundary launches
+        const int S = (int)m->segs.size();
+        std::vector<SpmvArgs> as(S, a);
+        std::vector<int> grids(S, 0);
+        int total = 0;
+        for (int i = 0; i < S; ++i) {
+            const PkSeg& sg = m->segs[i];
+            as[i].rowptr = sg.rp32 - sg.row_lo;           // indexed by the absolute row
+            as[i].col = m->col + sg.base;
+            as[i].val = m->val + sg.base;
+            as[i].nnz_total = sg.nnz;
+            as[i].rowptr_len = sg.row_hi + 1;
+            as[i].base_mis = (int)(sg.base & 3);
+            as[i].row_lo = sg.row_lo;
+            as[i].row_hi = sg.row_hi;
+            PK_CHECK(launch_stream_any(ctx, m, two, as[i], ra, &grids[i], ctx->red.max_blocks / S, 1));
+            total += grids[i];
+        }
+        int off = 0;
+        for (int i = 0; i < S; ++i) {
+            PkRedArgs rs = ra;
+            rs.block_off = off;
+            rs.nb_total = total;
+            rs.store_only = (i + 1 < S) ? 1 : 0;
+            if (grids[i] > 0) PK_CHECK(launch_stream_any(ctx, m, two, as[i], rs, &grids[i], ctx->red.max_blocks / S, 2));
+            off += grids[i];
+        }
+    } else if (!exchange) {
         a.row_lo = 0; a.row_hi = m->n_rows;
         PK_CHECK(launch_stream_any(ctx, m, two, a, ra, &grid, ctx->red.max_blocks, 0));
     } else if (m->halo_p2p && m->use_tma && !m->pat_on) {

@@ -1,5 +1,6 @@
 """GPU parity of the individual kernels (through the C-ABI) against the oracle's numpy/scipy operations."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -8,6 +9,7 @@ import torch
 from parallel_krylov_b200 import problems
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -208,3 +210,66 @@ def test_solvers_on_compressed_operator_match_csr_bitwise(pk, solver, k):
     np.testing.assert_allclose(x1.cpu().numpy(), x0.cpu().numpy(), rtol=1e-8, atol=1e-12)
     if solver == "kskipcg":          # no dot product comes out of an SpMV epilogue in this solver: identical bits
         assert torch.equal(x0, x1)
+
+
+@pytest.mark.parametrize("n,half_bw,k", [(30011, 13, 8), (5000, 2, 4), (700, 13, 2), (100003, 13, 5)])
+def test_matrix_powers_one_pass_is_bitwise_k_sequential_spmvs(pk, n, half_bw, k):
+    """k levels of both basis chains in ONE pass over A (csrc/pk_matpow.cu) == k sequential operator applications,
+    bit for bit (same per-row left-to-right sums) — including windows cut by the matrix ends."""
+    import ctypes as C
+    from parallel_krylov_b200 import _lib
+    from parallel_krylov_b200._core import _ptr
+    A = problems.to_scipy(*problems.banded_spd(n, half_bw, 1))
+    op = pk.Operator.from_any(A)
+    ctx, ld = op.ctx, op.ld
+    rng = np.random.default_rng(k)
+    u0, v0 = rng.standard_normal(n), rng.standard_normal(n)
+    U = torch.zeros((k + 1) * ld, dtype=torch.float64, device="cuda")
+    V = torch.zeros((k + 1) * ld, dtype=torch.float64, device="cuda")
+    U[:n] = torch.from_numpy(u0).cuda()
+    V[:n] = torch.from_numpy(v0).cuda()
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.pk_matpow(ctx.handle, op.handle, k, _ptr(U), _ptr(V)), "pk_matpow")
+    ctx.sync()
+    u, v = u0, v0
+    for l in range(1, k + 1):
+        u, v = A.dot(u), A.dot(v)               # == op.matvec, which is bit-identical to scipy (test above)
+        assert np.array_equal(U[l * ld:l * ld + n].cpu().numpy(), u), f"chain 0 level {l}"
+        assert np.array_equal(V[l * ld:l * ld + n].cpu().numpy(), v), f"chain 1 level {l}"
+
+
+def test_matrix_powers_refuses_wide_operators(pk):
+    import ctypes as C
+    from parallel_krylov_b200 import _lib
+    from parallel_krylov_b200._core import _ptr
+    A = problems.to_scipy(*problems.poisson3d(20))         # half bandwidth 400: no one-pass basis
+    op = pk.Operator.from_any(A)
+    buf = torch.zeros(4 * op.ld, dtype=torch.float64, device="cuda")
+    assert op.ctx.lib.pk_matpow(op.ctx.handle, op.handle, 2, _ptr(buf), _ptr(buf)) == -4      # PK_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("solver,k", [("kskipmrr", 8), ("kskipcg", 4), ("adaptivekskipmrr", 8)])
+def test_solvers_with_and_without_matrix_powers_agree_bitwise(pk, solver, k):
+    """The one-pass basis changes no bit of a solve (run in a subprocess with PK_MATPOW=0 for the reference run)."""
+    import subprocess
+    import sys
+    A = problems.to_scipy(*problems.banded_spd(20000, 13, 0))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    x, info = getattr(pk, solver)(A, b, tol=1e-8, k=k)
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import parallel_krylov_b200 as pk\n"
+        "from parallel_krylov_b200 import problems\n"
+        "A = problems.to_scipy(*problems.banded_spd(20000, 13, 0)); b = problems.rhs(A.shape[0], 'randn', 0)\n"
+        f"x, info = pk.{solver}(A, b, tol=1e-8, k={k})\n"
+        "np.save(sys.argv[1], np.concatenate([x.cpu().numpy(), info['residual'].cpu().numpy()]))\n")
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "ref.npy")
+        env = dict(os.environ, PK_MATPOW="0", PK_QUIET="1")
+        r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ref = np.load(out)
+    got = np.concatenate([x.cpu().numpy(), info["residual"].cpu().numpy()])
+    assert np.array_equal(got, ref)
