@@ -851,6 +851,8 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     s.method = method;
     ctx->launches = 0;
     ctx->spmvs = 0;
+    // structure probe of the one-pass basis kernel: synchronises once per operator, so it must happen before any capture
+    if (method == PK_KSKIPCG || method == PK_KSKIPMRR || method == PK_ADAPTIVEKSKIPMRR) (void)pk_matpow_ok(ctx, mat, opts->k);
     PK_CHECK(s.init_state(d_residual, d_nosl, method == PK_ADAPTIVEKSKIPMRR ? d_khistory : nullptr, hist_len));
     int final_k = opts->k;
     int rc = PK_OK;
