@@ -880,32 +880,52 @@ __global__ void __launch_bounds__(BLOCK) k_gemv_staged(GemvArgs a, PkRedArgs ra)
         double s0[R], s1[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { s0[r] = 0.0; s1[r] = 0.0; }
+        // Software pipeline over the whole row, independent of the x chunks: two register buffers of A (this lane's
+        // columns c2 and c2 + 32, as double2); while one is consumed the other's loads — and the reload of the first —
+        // are in flight.  (ncu r02: with the loads left to the compiler the 80-register budget made it load two
+        // vectors, wait, compute, load two more: 62 % of HBM peak, every sample a long-scoreboard stall on the first DMUL.)
+        const long long n2 = a.n_cols >> 1;
+        long long c2 = lane;
+        double2 a0[R], a1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            a0[r] = (c2 < n2) ? __ldg(ar2[r] + c2) : make_double2(0.0, 0.0);
+            a1[r] = (c2 + 32 < n2) ? __ldg(ar2[r] + c2 + 32) : make_double2(0.0, 0.0);
+        }
+        auto consume = [&](const double2 (&av)[R], const double2 xv, const double2 xw) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                s0[r] += av[r].x * xv.x;
+                s0[r] += av[r].y * xv.y;
+                if (NV == 2) {
+                    s1[r] += av[r].x * xw.x;
+                    s1[r] += av[r].y * xw.y;
+                }
+            }
+        };
         for (long long ch = 0; ch < n_chunks; ++ch, ++v) {
             const int s = (int)(v % STAGES);
             if (tid == 0 && v + STAGES - 1 < total) issue(v + STAGES - 1);
             mbar_wait(&full[s], (unsigned)((v / STAGES) & 1));
-            const long long c0 = ch * CW;
-            const int w2 = (int)((a.n_cols - c0 < CW ? a.n_cols - c0 : CW) >> 1);    // double2 elements in this chunk
+            const long long cb = (ch * CW) >> 1;                                     // first double2 column of the chunk
+            const long long ce = (cb + CW / 2 < n2) ? cb + CW / 2 : n2;              // one past its last
             const double2* x02 = reinterpret_cast<const double2*>(xs + ((size_t)s * NV + 0) * CW);
             const double2* x12 = reinterpret_cast<const double2*>(xs + ((size_t)s * NV + 1) * CW);
-            const long long cb = c0 >> 1;
-#pragma unroll 2
-            for (int c = lane; c < w2; c += 32) {
-                double2 av[R];
+            // (a pair c2, c2 + 32 never straddles a full-chunk boundary: chunks hold a multiple of 64 double2 columns)
+            while (c2 < ce) {
+                consume(a0, x02[c2 - cb], NV == 2 ? x12[c2 - cb] : make_double2(0.0, 0.0));
+                if (c2 + 64 < n2) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) av[r] = __ldg(ar2[r] + cb + c);
-                const double2 xv = x02[c];
-                double2 xw = make_double2(0.0, 0.0);
-                if (NV == 2) xw = x12[c];
+                    for (int r = 0; r < R; ++r) a0[r] = __ldg(ar2[r] + c2 + 64);
+                }
+                if (c2 + 32 < ce) {
+                    consume(a1, x02[c2 + 32 - cb], NV == 2 ? x12[c2 + 32 - cb] : make_double2(0.0, 0.0));
+                    if (c2 + 96 < n2) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    s0[r] += av[r].x * xv.x;
-                    s0[r] += av[r].y * xv.y;
-                    if (NV == 2) {
-                        s1[r] += av[r].x * xw.x;
-                        s1[r] += av[r].y * xw.y;
+                        for (int r = 0; r < R; ++r) a1[r] = __ldg(ar2[r] + c2 + 96);
                     }
                 }
+                c2 += 64;
             }
             __syncthreads();          // the stage may be refilled by the next visit's issue
         }

@@ -63,9 +63,17 @@ def test_solver_matches_reference_golden(pk, case):
         assert true_res < case["tol"] * (1.0 + 1e-6) or true_res < 1.05 * gold["true_relres"], true_res
         # recorded final residual is the true residual to a few digits
         assert abs(info["residual"][-1] - true_res) <= 1e-3 * true_res + 1e-14
+    if tol_h is None and kskip and not chaotic:
+        # k >= 5: the unscaled monomial basis makes late trips rounding-sensitive, but the opening step
+        # and the first two trips are still comparable — at a loose tolerance instead of not at all
+        m2 = min(4, len(info["residual"]), len(gold["residual"]))
+        np.testing.assert_allclose(info["residual"][:m2], gold["residual"][:m2], rtol=1e-6)
+        assert np.array_equal(info["nosl"][:m2], gold["nosl"][:m2])
     if "khistory" in gold and not chaotic:
-        assert np.array_equal(info["khistory"], gold["khistory"][: len(info["khistory"])]) or \
-            len(info["khistory"]) != len(gold["khistory"])
+        # strict on the common prefix (the runs may differ by one trip at the very end, never in k on these systems)
+        mk = min(len(info["khistory"]), len(gold["khistory"]))
+        assert mk >= min(len(gold["khistory"]), 2)
+        assert np.array_equal(info["khistory"][:mk], gold["khistory"][:mk])
     if "x" in gold and tol_h is not None and not capped and it == it_ref:
         np.testing.assert_allclose(x, gold["x"], rtol=1e-6, atol=1e-8 * np.abs(gold["x"]).max())
 
