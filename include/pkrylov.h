@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PK_VERSION 101
+#define PK_VERSION 102
 #define PK_KMAX 32            /* largest k of the k-skip solvers */
 #define PK_NCCL_ID_BYTES 128
 #define PK_IPC_HANDLE_BYTES 64
@@ -164,6 +164,10 @@ typedef struct {
     int32_t x_is_zero;     /* 1: x0 == 0, skip the initial A·x (result identical: b - A·0 == b)                   */
     int64_t global_n;      /* global number of rows (== n_rows when not distributed)                             */
     const double* d_mdiag; /* PK_CGCG only: diagonal of the Jacobi preconditioner M (local rows), u = r / M; NULL = none  */
+    int32_t basis;         /* PK_KSKIPMRR only: 0 = the reference's monomial basis A^j r (default, parity path);
+                              1 = Chebyshev basis T_j((A - d)/c) r on [lam_lo, lam_hi] (opt-in)         */
+    int32_t pad0;
+    double lam_lo, lam_hi; /* basis = 1: bounds of the spectrum of A (pk_mat_gershgorin gives rigorous ones)                */
 } pk_solve_opts;
 
 typedef struct {
@@ -179,6 +183,10 @@ typedef struct {
 
 /* d_out[i] = A[i][i] for the local rows (0 where the row stores no diagonal entry): the Jacobi preconditioner of PK_CGCG. */
 int pk_mat_diagonal(pk_mat* mat, double* d_out);
+
+/* Gershgorin bounds of the spectrum from the local rows: h_out[0] = min_i (a_ii - sum_{j != i} |a_ij|),
+ * h_out[1] = max_i (a_ii + sum_{j != i} |a_ij|) (host doubles; blocking).  Distributed: min / max over the ranks' results. */
+int pk_mat_gershgorin(pk_mat* mat, double* h_out);
 
 /* Number of doubles of scratch (d_work) the solver needs for vectors of padded length `ld`. */
 int64_t pk_work_doubles(int method, int64_t ld, int k);

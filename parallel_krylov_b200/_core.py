@@ -358,7 +358,7 @@ def quiet() -> bool:
 
 def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_every: int = 0,
           use_graph: Optional[bool] = None, verbose: Optional[bool] = None, ctx: Optional[Context] = None,
-          compress: Optional[bool] = None, M=None):
+          compress: Optional[bool] = None, M=None, basis=None):
     """Shared body of the five entry points.  Returns ``(x, info)`` like the reference
     (/root/reference/v3/gpu/cg.py:47-52): x and the histories are torch CUDA tensors."""
     op = Operator.from_any(A, ctx)
@@ -425,10 +425,34 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
             if mt.numel() != n:
                 raise PkError(f"M has {mt.numel()} entries; expected the diagonal for {n} local rows")
             mdiag = mt.to(device=dev, dtype=torch.float64).contiguous()
+    # Basis of the k-skip trips (kskipmrr): None / "monomial" = the reference's A^j r (parity path, default);
+    # "chebyshev" = T_j((A - d)/c) r on Gershgorin bounds of the spectrum, or ("chebyshev", lam_lo, lam_hi) with bounds
+    # of the caller's — numerically safe at k = 8, 12, 16 where the monomial basis is not (opt-in).
+    basis_id, lam_lo, lam_hi = 0, 0.0, 0.0
+    if basis is not None and basis != "monomial":
+        name = basis if isinstance(basis, str) else basis[0]
+        if name != "chebyshev" or method != "kskipmrr":
+            raise PkError(f"basis={basis!r}: only 'chebyshev' for kskipmrr (or None / 'monomial')")
+        basis_id = 1
+        if isinstance(basis, str):
+            bounds = (C.c_double * 2)()
+            with torch.cuda.device(ctx.device):
+                check(lib.pk_mat_gershgorin(op.handle, bounds), "pk_mat_gershgorin")
+            lam_lo, lam_hi = float(bounds[0]), float(bounds[1])
+            if ctx.n_ranks > 1:
+                import torch.distributed as dist
+                t = torch.tensor([-lam_lo, lam_hi], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=ctx.group)
+                lam_lo, lam_hi = -float(t[0].item()), float(t[1].item())
+        else:
+            lam_lo, lam_hi = float(basis[1]), float(basis[2])
+        if not lam_hi > lam_lo:
+            raise PkError(f"Chebyshev basis: need lam_lo < lam_hi, got [{lam_lo}, {lam_hi}]")
     opts = SolveOpts(maxiter=maxiter, tol=float(tol), k=k, check_every=int(check_every),
                      use_graph=1 if (use_graph if use_graph is not None else True) else 0,
                      x_is_zero=1 if x_is_zero else 0, global_n=op.n_global,
-                     d_mdiag=mdiag.data_ptr() if mdiag is not None else None)
+                     d_mdiag=mdiag.data_ptr() if mdiag is not None else None,
+                     basis=basis_id, lam_lo=lam_lo, lam_hi=lam_hi)
     res = SolveResult()
     show = (not quiet()) if verbose is None else verbose
     if show and ctx.rank == 0:

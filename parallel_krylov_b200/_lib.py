@@ -22,7 +22,8 @@ METHOD_IDS = {"cg": PK_CG, "mrr": PK_MRR, "kskipcg": PK_KSKIPCG, "kskipmrr": PK_
 
 class SolveOpts(C.Structure):
     _fields_ = [("maxiter", C.c_int64), ("tol", C.c_double), ("k", C.c_int32), ("check_every", C.c_int32),
-                ("use_graph", C.c_int32), ("x_is_zero", C.c_int32), ("global_n", C.c_int64), ("d_mdiag", C.c_void_p)]
+                ("use_graph", C.c_int32), ("x_is_zero", C.c_int32), ("global_n", C.c_int64), ("d_mdiag", C.c_void_p),
+                ("basis", C.c_int32), ("pad0", C.c_int32), ("lam_lo", C.c_double), ("lam_hi", C.c_double)]
 
 
 class SolveResult(C.Structure):
@@ -68,6 +69,7 @@ _SIGS = {
     "pk_gram": (C.c_int, [_P, C.c_int, _I64, _I64, _P, C.c_int, _P, C.c_int, _P]),
     "pk_work_doubles": (_I64, [C.c_int, _I64, C.c_int]),
     "pk_mat_diagonal": (C.c_int, [_P, _P]),
+    "pk_mat_gershgorin": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "pk_solve": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(SolveOpts),
                            C.POINTER(SolveResult)]),
     "pk_gen_stencil_counts": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P]),

@@ -223,6 +223,61 @@ __global__ void k_csr_diag(const int32_t* __restrict__ rowptr, const int32_t* __
     }
 }
 
+// Gershgorin discs of the local rows: lo = min_i (a_ii - R_i), hi = max_i (a_ii + R_i), R_i = sum_{j != i} |a_ij|.
+// Doubles are reduced with integer atomics on an order-preserving key.
+__device__ __forceinline__ unsigned long long pk_ord_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_gershgorin_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                 const double* __restrict__ val, long long n_rows, long long row0,
+                                 unsigned long long* __restrict__ keys) {
+    double lo = 1e300, hi = -1e300;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        double d = 0.0, off = 0.0;
+        for (int q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+            const double v = val[q];
+            if (col[q] == (int)(r + row0)) d += v; else off += fabs(v);
+        }
+        lo = fmin(lo, d - off);
+        hi = fmax(hi, d + off);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys, pk_ord_key(lo));
+        atomicMax(keys + 1, pk_ord_key(hi));
+    }
+}
+__global__ void k_gershgorin_dense(const double* __restrict__ a, long long lda, long long n_rows, long long n_cols,
+                                   unsigned long long* __restrict__ keys) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < n_rows; r += nwarps) {
+        double off = 0.0;
+        for (long long c = lane; c < n_cols; c += 32)
+            if (c != r) off += fabs(a[r * lda + c]);
+        for (int o = 16; o > 0; o >>= 1) off += __shfl_down_sync(0xffffffffu, off, o);
+        if (lane == 0) {
+            const double d = a[r * lda + r];
+            atomicMin(keys, pk_ord_key(d - off));
+            atomicMax(keys + 1, pk_ord_key(d + off));
+        }
+    }
+}
+
+// out = s1 * a + s2 * b  (Chebyshev basis: U_1 = (A r - d r) / c from the A r the previous step left behind)
+__global__ void __launch_bounds__(EW_BLOCK) k_axpby(long long n, double s1, const double* __restrict__ a, double s2,
+                                                    const double* __restrict__ b, double* __restrict__ out,
+                                                    const PkState* st) {
+    if (pk_done(st)) return;
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) out[i] = s1 * a[i] + s2 * b[i];
+}
+
 __global__ void k_dense_diag(const double* __restrict__ a, long long lda, long long n_rows, double* __restrict__ out) {
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
         out[r] = a[r * lda + r];
@@ -548,6 +603,42 @@ extern "C" int pk_mat_diagonal(pk_mat* m, double* d_out) {
             k_csr_diag<<<grid, 256, 0, ctx->stream>>>(sg.rp32, m->col + sg.base, m->val + sg.base, sg.row_hi - sg.row_lo,
                                                       sg.row_lo, d_out + sg.row_lo);
     PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+int pk_launch_axpby(pk_ctx* ctx, long long n, double s1, const double* a, double s2, const double* b, double* out) {
+    k_axpby<<<ew_grid(ctx, k_axpby, n), EW_BLOCK, 0, ctx->stream>>>(n, s1, a, s2, b, out, ctx->d_state);
+    PK_LAUNCH_CHECK();
+    return PK_OK;
+}
+
+extern "C" int pk_mat_gershgorin(pk_mat* m, double* h_out) {
+    PK_REQUIRE(m && h_out, "null argument");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    unsigned long long h[2] = {~0ull, 0ull};
+    PK_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    PK_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    int grid = (int)((m->n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    if (grid < 1) grid = 1;
+    if (m->kind == MAT_DENSE) k_gershgorin_dense<<<grid, 256, 0, ctx->stream>>>(m->dense, m->lda, m->n_rows, m->n_cols, d);
+    else if (m->segs.empty()) k_gershgorin_csr<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->val, m->n_rows, 0, d);
+    else
+        for (const PkSeg& sg : m->segs)
+            k_gershgorin_csr<<<grid, 256, 0, ctx->stream>>>(sg.rp32, m->col + sg.base, m->val + sg.base,
+                                                            sg.row_hi - sg.row_lo, sg.row_lo, d);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    for (int i = 0; i < 2; ++i) {
+        const unsigned long long k = h[i];
+        const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+        long long bits = (long long)b;
+        memcpy(&h_out[i], &bits, sizeof(double));
+    }
     return PK_OK;
 }
 

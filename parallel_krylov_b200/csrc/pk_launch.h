@@ -21,6 +21,7 @@ int pk_launch_mrr_update(pk_ctx* ctx, long long n, const double* ar, double* y, 
                          double* r_out, double* r_alt, double* x, int cj, int epi);
 int pk_launch_cgcg_update(pk_ctx* ctx, long long n, double* x, double* r, double* u, const double* w, double* p,
                           double* s, const double* mdiag, int init);
+int pk_launch_axpby(pk_ctx* ctx, long long n, double s1, const double* a, double s2, const double* b, double* out);
 int pk_launch_adapt_save(pk_ctx* ctx, long long n, double* x, double* best_x);
 int pk_launch_kscg_update(pk_ctx* ctx, long long n, double* x, double* ar0, const double* ap0, double* ap0_out,
                           const double* ap1, int cj, int epi);
@@ -32,8 +33,11 @@ struct PkDots {
     const double* w = nullptr;   // sums: [0] = w.y, [1] = y.y, [2] = w.w   (nullptr: no reduction)
     int epi = EPI_NONE;
     int extra_sums = 0;          // st->red[3 .. 3+extra) hold local sums of an EARLIER kernel: all-reduce them with these
-    // k-skip step fused into the row epilogue (see SpmvArgs in pk_spmv.cu); only the TMA CSR kernel supports it
+    // k-skip step fused into the row epilogue (see SpmvArgs in pk_spmv.cu); only the TMA CSR kernel supports it.
+    // fuse = 3 (two right-hand sides): three-term recurrence of the Chebyshev basis in the epilogue,
+    //   y0 = cs[0] (A x0) + cs[1] x0 + cs[2] f_a ;  y1 = cs[3] (A x1) + cs[4] x1 + cs[5] f_b   (f_a / f_b may be null)
     int fuse = 0, cj = 0;
+    double cs[6] = {0, 0, 0, 0, 0, 0};
     double* f_a = nullptr;
     double* f_b = nullptr;
     double* f_x = nullptr;

@@ -84,3 +84,57 @@ PK_HD inline void pk_kskipmrr_coef(const double* G, int k, double* coef) {
         coef[2 * (j + 1) + 1] = eta;
     }
 }
+
+
+// ---- k-skip MrR on a CHEBYSHEV basis (opt-in, SURVEY.md §8f rank 3: numerically safer k-skip) -------------------------
+// The reference builds its trip from the moments (r, A^l r), (y, A^l r), (y, A^l y) of the unscaled monomial basis
+// (/root/reference/v3/cpu/kskipmrr.py:45-59), whose entries span rho(A)^(2k) and whose vectors become parallel: at k = 8
+// its history already differs from plain MrR in the third digit and k >= 12 is chaotic.  Here the basis vectors are
+// U_j = T_j(Ah) r, V_j = T_j(Ah) y with Ah = (A - d I) / c mapping [lam_lo, lam_hi] (Gershgorin bounds of A) to [-1, 1];
+// the SAME six near-diagonal Gram sums per level give the Chebyshev moments through T_a T_b = (T_{a+b} + T_{|a-b|}) / 2
+// (A symmetric):   m_{2j} = 2 (T_j u, T_j w) - m_0,   m_{2j+1} = 2 (T_j u, T_{j+1} w) - m_1,
+// and the reference's step recurrences (kskipmrr.py:72-84) carry over with "multiply by A" — an index shift on monomial
+// moments — replaced by   (u, T_l A w) = c (m_{l+1} + m_{|l-1|}) / 2 + d m_l.
+// Same iterates as MrR in exact arithmetic; in fp64 the k = 8 and k = 12 histories of the Poisson systems agree with plain
+// MrR to ~1e-15 (tests/test_chebyshev_basis.py).  G has the layout of pk_kskipmrr_coef (U = T_j r rows, V = T_j y rows).
+PK_HD inline void pk_cheb_mulA(const double* m, int L, double c, double d, double* out) {   // out[0..L) from m[0..L]
+    out[0] = c * m[1] + d * m[0];
+    for (int l = 1; l < L; ++l) out[l] = (c * (m[l + 1] + m[l - 1])) / 2.0 + d * m[l];
+}
+
+PK_HD inline void pk_kskipmrr_coef_cheb(const double* G, int k, double c, double d, double* coef) {
+    double al[2 * PK_KMAX + 3], be[2 * PK_KMAX + 2], de[2 * PK_KMAX + 1];
+    double Aal[2 * PK_KMAX + 3], AAal[2 * PK_KMAX + 3], Abe[2 * PK_KMAX + 2];
+    // Chebyshev moments from the Gram sums: al_l = (r, T_l r), be_l = (y, T_l r), de_l = (y, T_l y)
+    al[0] = G[0];                          // U0.U0
+    al[1] = G[1];                          // U0.U1
+    for (int j = 2; j < 2 * k + 3; ++j) al[j] = 2.0 * G[6 * (j >> 1) + (j & 1)] - al[j & 1];
+    be[0] = G[2];                          // U0.V0
+    be[1] = G[3];                          // V0.U1
+    for (int j = 2; j < 2 * k + 2; ++j) be[j] = 2.0 * G[6 * (j >> 1) + 2 + (j & 1)] - be[j & 1];
+    de[0] = G[4];                          // V0.V0
+    if (k >= 1) de[1] = G[5];              // V0.V1
+    for (int j = 2; j < 2 * k + 1; ++j) de[j] = 2.0 * G[6 * (j >> 1) + 4 + (j & 1)] - de[j & 1];
+    int Ld = 2 * k + 1;                    // valid lengths: al Ld + 2, be Ld + 1, de Ld
+    for (int j = 0; j <= k; ++j) {
+        pk_cheb_mulA(al, Ld + 1, c, d, Aal);        // (r, T_l A r),    l < Ld + 1
+        pk_cheb_mulA(Aal, Ld, c, d, AAal);          // (r, T_l A^2 r),  l < Ld
+        pk_cheb_mulA(be, Ld, c, d, Abe);            // (y, T_l A r),    l < Ld
+        const double a1 = Aal[0], a2 = AAal[0], b1 = Abe[0], d0 = de[0];
+        const double dd = a2 * d0 - b1 * b1;        // kskipmrr.py:62-64 / :86-88
+        const double zeta = (a1 * d0) / dd;
+        const double eta = ((-a1) * b1) / dd;
+        coef[2 * j] = zeta;
+        coef[2 * j + 1] = eta;
+        if (j == k) break;
+        for (int l = 0; l < Ld; ++l) {              // kskipmrr.py:72-84 on Chebyshev moments
+            const double den = (PK_SQ(eta) * de[l] + ((2.0 * eta) * zeta) * Abe[l]) + PK_SQ(zeta) * AAal[l];
+            const double tau = eta * be[l] + zeta * Aal[l];
+            const double ben = tau - den;
+            al[l] = al[l] - (tau + ben);
+            be[l] = ben;
+            de[l] = den;
+        }
+        Ld -= 2;                                    // al keeps Ld + 2, be Ld + 1, de Ld valid entries
+    }
+}

@@ -435,7 +435,7 @@ extern "C" int64_t pk_work_doubles(int method, int64_t ld, int k) {
         case PK_CG: nvec = 3; break;                       // r, p, v
         case PK_MRR: nvec = 4; break;                      // r, Ar, y, z
         case PK_KSKIPCG: nvec = (k + 1) + (k + 2) + 1; break;  // Ar[0..k], Ap[0..k+1], spare Ap0 (fused steps)
-        case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 2; break;          // Ar[0..k+1], Ay[0..k], z, spare Ar0
+        case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;          // Ar[0..k+1], Ay[0..k], z, spare Ar0, A r (Chebyshev basis)
         case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;  // + best_x
         case PK_CGCG: nvec = 5; break;                     // r, w, p, s, u (u aliases r without a preconditioner)
         default: return -1;
@@ -789,11 +789,64 @@ struct Solve {
     }
     int kskipmrr() {
         const int k = o.k;
+        if (o.basis == 1) return kskipmrr_chebyshev();
         double *Ar0 = vec(0), *Ar1 = vec(1), *Ay0 = vec(k + 2), *z = vec(2 * k + 3);
         PK_CHECK(initial_residual(Ar0, nullptr, Ar1, EPI_RES0));
         PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         PK_CHECK(kskipmrr_open(Ar0, Ar1, Ay0, z, EPI_KS_FIRST));
         PK_CHECK(run_batches(k + 1, 1, [&]() -> int { return kskipmrr_trip(k, k); }));
+        return PK_OK;
+    }
+
+    // ---- k-skip MrR on a Chebyshev basis (opt-in; pk_scalars.h: pk_kskipmrr_coef_cheb) -------------
+    // Same loop as kskipmrr(): only the basis of a trip (U_j = T_j(Ah) r, V_j = T_j(Ah) y instead of A^j r, A^j y; the
+    // three-term recurrence rides in the epilogue of the two-chain SpMV) and the scalar engine's moment recurrences differ.
+    // The k+1 steps of a trip are the same fused update + SpMV kernels, fed with (zeta_j, eta_j) computed from Chebyshev
+    // moments.  A r of the current residual lives in its own vector (AR): level 1 of the basis is no longer A r.
+    int kskipmrr_chebyshev() {
+        const int k = o.k;
+        PK_REQUIRE(o.lam_hi > o.lam_lo, "Chebyshev basis needs spectrum bounds lam_lo < lam_hi (pk_mat_gershgorin)");
+        PK_REQUIRE(A->kind != MAT_DENSE && A->use_tma && !A->pat_on,
+                   "the Chebyshev basis needs the TMA CSR kernel (16-byte aligned CSR arrays, no pattern compression)");
+        const double c = 0.5 * (o.lam_hi - o.lam_lo), d = 0.5 * (o.lam_hi + o.lam_lo);
+        auto U = [&](int j) { return vec(j); };                   // rows 0..k+1, U(0) = r
+        auto V = [&](int j) { return vec(k + 2 + j); };           // rows 0..k,   V(0) = y
+        double *z = vec(2 * k + 3), *spare = vec(2 * k + 4), *AR = vec(2 * k + 5);
+        {   // c, d into the device state before anything reads them
+            PkState* h = ctx->h_state;
+            h->cheb_c = c;
+            h->cheb_d = d;
+            PK_CUDA(cudaMemcpyAsync(&ctx->d_state->cheb_c, &h->cheb_c, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        PK_CHECK(initial_residual(U(0), nullptr, AR, EPI_RES0));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(kskipmrr_open(U(0), AR, V(0), z, EPI_KS_FIRST));      // opening MrR step; leaves AR = A r
+        PK_CHECK(run_batches(k + 1, 1, [&]() -> int {
+            // basis: U_1 = (A r - d r) / c from the A r at hand, then per level one pass over A for both chains
+            PK_CHECK(pk_launch_axpby(ctx, n, 1.0 / c, AR, -d / c, U(0), U(1)));
+            for (int j = 1; j <= k; ++j) {
+                PkDots dd;
+                dd.fuse = 3;
+                dd.cs[0] = 2.0 / c; dd.cs[1] = -2.0 * d / c; dd.cs[2] = -1.0;          // U_{j+1} = 2 Ah U_j - U_{j-1}
+                dd.f_a = U(j - 1);
+                if (j == 1) { dd.cs[3] = 1.0 / c; dd.cs[4] = -d / c; dd.cs[5] = 0.0; dd.f_b = nullptr; }   // V_1 = Ah V_0
+                else { dd.cs[3] = 2.0 / c; dd.cs[4] = -2.0 * d / c; dd.cs[5] = -1.0; dd.f_b = V(j - 2); }
+                PK_CHECK(pk_launch_spmv(ctx, A, U(j), U(j + 1), V(j - 1), V(j), dd));
+            }
+            PK_CHECK(pk_launch_gram(ctx, 0, n, ld, U(0), k + 2, V(0), k + 1, k + 2, EPI_GRAM_MRR_CHEB));
+            // the k+1 steps: as in kskipmrr_trip (fused: A r of the step lives in registers; r ping-pongs home <-> spare)
+            double* cur = (k % 2 == 1) ? spare : U(0);
+            PK_CHECK(pk_launch_mrr_update(ctx, n, AR, V(0), z, U(0), cur, nullptr, x, 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
+            for (int j = 1; j <= k; ++j) {
+                double* nxt = (cur == spare) ? U(0) : spare;
+                PkDots ds;
+                ds.epi = (j == k) ? EPI_KS_TRIP_END : EPI_KS_STEP;
+                ds.fuse = 1; ds.cj = j; ds.f_a = V(0); ds.f_b = z; ds.f_x = x; ds.f_out = nxt;
+                PK_CHECK(pk_launch_spmv(ctx, A, cur, nullptr, nullptr, nullptr, ds));
+                cur = nxt;
+            }
+            return apply(U(0), AR);                                   // cur == U(0): A r for the next trip
+        }));
         return PK_OK;
     }
 

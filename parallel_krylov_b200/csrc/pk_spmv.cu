@@ -55,7 +55,8 @@ struct SpmvArgs {
     //   fuse 1 (MrR, x0 = Ar0): Ay0 = eta Ay0 + zeta y ; z = eta z - zeta Ar0 ; Ar0' = Ar0 - Ay0 ; x -= z   (y = A Ar0 not stored)
     //   fuse 2 (CG,  x0 = Ap0): x += alpha Ap0 ; Ar0 -= alpha y ; Ap0' = Ar0 + beta Ap0                    (y = A Ap0 not stored)
     int fuse, cj;
-    double* f_a;            // MrR: Ay0      | CG: Ar0 (in place)
+    double cs[6];           // fuse 3: coefficients of the three-term recurrence (see PkDots)
+    double* f_a;            // MrR: Ay0      | CG: Ar0 (in place)    | fuse 3: previous level of chain 0 (nullable)
     double* f_b;            // MrR: z        | CG: unused
     double* f_x;            // solution x
     double* f_out;          // MrR: Ar0'     | CG: Ap0'   (a buffer different from x0: other rows still gather x0)
@@ -213,9 +214,9 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc[3] = {0.0, 0.0, 0.0};
-    const double c0 = FUSE ? ra.st->coef[2 * a.cj] : 0.0;       // zeta | alpha
-    const double c1 = FUSE ? ra.st->coef[2 * a.cj + 1] : 0.0;   // eta  | beta
-    if (FUSE && ra.dyn_cj >= 0) {
+    const double c0 = (FUSE == 1 || FUSE == 2) ? ra.st->coef[2 * a.cj] : 0.0;       // zeta | alpha
+    const double c1 = (FUSE == 1 || FUSE == 2) ? ra.st->coef[2 * a.cj + 1] : 0.0;   // eta  | beta
+    if ((FUSE == 1 || FUSE == 2) && ra.dyn_cj >= 0) {
         // k lives on the device (adaptive): the host passed x0 = home and f_out = spare of the ping-pong pair; step cj
         // reads the home buffer iff (k - cj + 1) is even, so that the last step of the trip (cj == k) writes home, and
         // only that last step reduces r.r and runs the trip-end epilogue
@@ -395,6 +396,10 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                 acc[1] += sum0 * sum0;
                 acc[2] += wi * wi;
             }
+        } else if (FUSE == 3) {           // Chebyshev basis level: T_{j+1} = 2 Ah T_j - T_{j-1}, Ah = (A - d) / c
+            // fa / fb: previous levels (0 when absent); xr / fx: the multiplied vectors' own entries of this row
+            a.y0[row] = (a.cs[0] * sum0 + a.cs[1] * xr) + a.cs[2] * fa;
+            if (NV == 2) a.y1[row] = (a.cs[3] * sum1 + a.cs[4] * fx) + a.cs[5] * fb;
         } else if (FUSE == 1) {           // kskipmrr.py:65-69 / :89-93 with (zeta, eta) = (c0, c1), Ar1 = sum0
             const double ay = c1 * fa + c0 * sum0;
             const double zz = c1 * fb - c0 * xr;
@@ -432,9 +437,9 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                 const long long row = r0 + tid;
                 // operands of the epilogue are requested before the row loop: their latency is hidden behind it
                 const double wi = (FUSE == 0 && a.w) ? __ldg(a.w + row) : 0.0;
-                const double fa = FUSE ? a.f_a[row] : 0.0;
-                const double fb = (FUSE == 1) ? a.f_b[row] : 0.0;
-                const double fx = FUSE ? a.f_x[row] : 0.0;
+                const double fa = (FUSE == 3) ? (a.f_a ? __ldg(a.f_a + row) : 0.0) : (FUSE ? a.f_a[row] : 0.0);
+                const double fb = (FUSE == 3) ? ((NV == 2 && a.f_b) ? __ldg(a.f_b + row) : 0.0) : ((FUSE == 1) ? a.f_b[row] : 0.0);
+                const double fx = (FUSE == 3) ? (NV == 2 ? __ldg(a.x1 + row) : 0.0) : (FUSE ? a.f_x[row] : 0.0);
                 const double xr = FUSE ? __ldg(a.x0 + row) : 0.0;
                 double sum0 = 0.0, sum1 = 0.0;
                 if (!BND) {
@@ -493,8 +498,12 @@ __global__ void __launch_bounds__(BLOCK) k_spmv_tma(SpmvArgs a, PkRedArgs ra) {
                 }
                 if (lane == 0) {
                     const long long row = r0 + r;
-                    finish_row(row, sum0, sum1, (FUSE == 0 && a.w) ? a.w[row] : 0.0, FUSE ? a.f_a[row] : 0.0,
-                               (FUSE == 1) ? a.f_b[row] : 0.0, FUSE ? a.f_x[row] : 0.0, FUSE ? a.x0[row] : 0.0);
+                    if (FUSE == 3)
+                        finish_row(row, sum0, sum1, 0.0, a.f_a ? a.f_a[row] : 0.0, (NV == 2 && a.f_b) ? a.f_b[row] : 0.0,
+                                   NV == 2 ? a.x1[row] : 0.0, a.x0[row]);
+                    else
+                        finish_row(row, sum0, sum1, (FUSE == 0 && a.w) ? a.w[row] : 0.0, FUSE ? a.f_a[row] : 0.0,
+                                   (FUSE == 1) ? a.f_b[row] : 0.0, FUSE ? a.f_x[row] : 0.0, FUSE ? a.x0[row] : 0.0);
                 }
             }
         }
@@ -1040,6 +1049,10 @@ int launch_tma(pk_ctx* ctx, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int g
 
 template <int NV, int BLOCK>
 int launch_tma_stages(pk_ctx* ctx, int stages, const SpmvArgs& a, PkRedArgs ra, int* grid_io, int cap, int mode) {
+    if (NV == 2 && a.fuse == 3) {
+        if (a.hrecv != nullptr) return launch_tma<2, BLOCK, 2, true, 3>(ctx, a, ra, grid_io, cap, mode);
+        return launch_tma<2, BLOCK, 2, false, 3>(ctx, a, ra, grid_io, cap, mode);
+    }
     if (NV == 1 && a.fuse == 1) {
         if (a.hrecv != nullptr) return launch_tma<1, BLOCK, 2, true, 1>(ctx, a, ra, grid_io, cap, mode);
         return launch_tma<1, BLOCK, 2, false, 1>(ctx, a, ra, grid_io, cap, mode);
@@ -1318,7 +1331,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.epi = dots.epi;
     ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;
     ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
-    ra.ar_n = dots.w ? 3 + dots.extra_sums : ((dots.fuse && dots.epi != EPI_KS_STEP) ? 1 : 0);
+    ra.ar_n = dots.w ? 3 + dots.extra_sums : (((dots.fuse == 1 || dots.fuse == 2) && dots.epi != EPI_KS_STEP) ? 1 : 0);
     ra.g_off = -1;
     ra.red_off = 0;
     ra.block_off = 0;
@@ -1348,6 +1361,9 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
     a.x0 = x; a.x1 = x1; a.y0 = y; a.y1 = y1; a.w = dots.w;
     a.fuse = dots.fuse; a.cj = dots.cj; a.f_a = dots.f_a; a.f_b = dots.f_b; a.f_x = dots.f_x; a.f_out = dots.f_out;
+    for (int i = 0; i < 6; ++i) a.cs[i] = dots.cs[i];
+    if (dots.fuse == 3) PK_REQUIRE(two && m->use_tma && !m->pat_on && m->kind != MAT_DENSE,
+                                   "the Chebyshev basis needs the TMA CSR kernel (16-byte aligned CSR arrays, no pattern compression)");
     a.nnz_total = m->nnz;
     a.rowptr_len = m->n_rows + 1;
     a.base_mis = 0;
@@ -1362,7 +1378,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         if (bl < 0) { const char* e = getenv("PK_TILE_ORDER"); bl = (e && strcmp(e, "blocked") == 0) ? 1 : 0; }
         a.blocked = bl;
     }
-    a.reduce = (dots.w || (dots.fuse && dots.epi != EPI_KS_STEP)) ? 1 : 0;
+    a.reduce = (dots.w || ((dots.fuse == 1 || dots.fuse == 2) && dots.epi != EPI_KS_STEP)) ? 1 : 0;
     int grid = 0;
 
     const bool exchange = m->distributed && (m->n_halo > 0 || (!m->send_off.empty() && m->send_off.back() > 0));
@@ -1443,6 +1459,6 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
         if (!waited) PK_CHECK(pk_comm_halo_wait(ctx));
     }
     if (dots.w) return pk_finish_reduce(ctx, 3 + dots.extra_sums, dots.epi, -1, 0);
-    if (dots.fuse && dots.epi != EPI_KS_STEP) return pk_finish_reduce(ctx, 1, dots.epi, -1, 0);
+    if ((dots.fuse == 1 || dots.fuse == 2) && dots.epi != EPI_KS_STEP) return pk_finish_reduce(ctx, 1, dots.epi, -1, 0);
     return PK_OK;
 }

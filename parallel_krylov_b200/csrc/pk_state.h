@@ -31,6 +31,7 @@ struct PkState {
     double gamma, alpha, beta, zeta, eta, mu, nu;
     double rr;            // ||r||^2 of the newest residual
     double best_res;      // adaptive: `pre_residual`, the smallest residual seen at a trip start
+    double cheb_c, cheb_d; // Chebyshev basis (opt-in): A = c Ah + d I maps [lam_lo, lam_hi] onto [-1, 1]
     // k-skip: coefficient pairs of the k+1 steps of one trip: (alpha_j, beta_j) or (zeta_j, eta_j)
     double coef[2 * (PK_KMAX + 1)];
     double gram[PK_GRAM_MAX];
@@ -69,6 +70,7 @@ enum PkEpi : int {
     EPI_ADAPT_GUARD,     // (no sums) loop condition, residual-growth guard, convergence test at the top of a trip
     EPI_CGCG_INIT,       // red[0] = u.w, red[3] = r.u          -> gamma, alpha = gamma/delta, beta = 0
     EPI_CGCG,            // red[0] = u.w, red[3] = r.u, red[4] = r.r -> it++, res[it], stop test, beta, alpha (one reduction/iteration)
+    EPI_GRAM_MRR_CHEB,   // gram[] of the Chebyshev basis complete -> coef[] = (zeta_j, eta_j)
 };
 
 
@@ -248,6 +250,9 @@ PK_HD inline void pk_epilogue(int epi, PkState* st) {
             break;
         case EPI_GRAM_MRR:
             if (GRAM) pk_kskipmrr_scalars(st);
+            break;
+        case EPI_GRAM_MRR_CHEB:
+            if (GRAM) pk_kskipmrr_coef_cheb(st->gram, st->k, st->cheb_c, st->cheb_d, st->coef);
             break;
         default:
             break;

@@ -25,14 +25,14 @@ def test_header_symbols_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in pkrylov.h but not exported by libpkrylov.so"
     assert set(_lib.exported_symbols()) == set(names), set(_lib.exported_symbols()) ^ set(names)
-    assert lib.pk_version() == 101
+    assert lib.pk_version() == 102
     assert lib.pk_work_doubles(0, 1024, 0) == 3 * 1024          # cg: r, p, v
-    assert lib.pk_work_doubles(3, 1024, 8) == (10 + 9 + 2) * 1024   # Ar, Ay, z, spare Ar0
+    assert lib.pk_work_doubles(3, 1024, 8) == (10 + 9 + 3) * 1024   # Ar, Ay, z, spare Ar0, A r
 
 
 def test_struct_layouts_match_header():
     from parallel_krylov_b200._lib import SolveOpts, SolveResult
-    assert ctypes.sizeof(SolveOpts) == 48 and ctypes.sizeof(SolveResult) == 56
+    assert ctypes.sizeof(SolveOpts) == 72 and ctypes.sizeof(SolveResult) == 56
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
