@@ -67,7 +67,14 @@ def test_solver_matches_reference_golden(pk, case):
         # k >= 5: the unscaled monomial basis makes late trips rounding-sensitive, but the opening step
         # and the first two trips are still comparable — at a loose tolerance instead of not at all
         m2 = min(4, len(info["residual"]), len(gold["residual"]))
-        np.testing.assert_allclose(info["residual"][:m2], gold["residual"][:m2], rtol=1e-6)
+        np.testing.assert_allclose(info["residual"][:min(m2, 2)], gold["residual"][:min(m2, 2)], rtol=1e-10)   # r0, opening step
+        for i in range(2, m2):
+            # a trip that shrinks the residual by orders of magnitude loses that many digits of its moments to cancellation
+            # (the reference run twice with different mat-vec summation orders differs by 1e-6 / 4e-5 on band5_777)
+            shrink = gold["residual"][i - 1] / gold["residual"][i]
+            rtol = 1e-6 if shrink < 100.0 else (1e-3 if shrink < 1e4 else None)
+            if rtol is not None:
+                np.testing.assert_allclose(info["residual"][i], gold["residual"][i], rtol=rtol)
         assert np.array_equal(info["nosl"][:m2], gold["nosl"][:m2])
     if "khistory" in gold and not chaotic:
         # strict on the common prefix (the runs may differ by one trip at the very end, never in k on these systems)
