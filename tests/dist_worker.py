@@ -74,6 +74,21 @@ def main():
     except AssertionError as e:
         failures.append(f"[cgcg jacobi rank {rank}] {e!r}"[:400])
 
+    # ---- opt-in Chebyshev basis, row-partitioned: k = 8 must follow plain MrR (Gershgorin bounds all-reduced over the ranks)
+    A = mats["p3d20"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
+    b = problems.rhs(n, "randn", 0)
+    xo, io = oracle.mrr(A, b.copy(), tol=1e-8)
+    x, info = pkm.kskipmrr(None, A[lo:hi], b, tol=1e-8, k=8, basis="chebyshev")
+    nosl = info["nosl"].cpu().numpy(); res = info["residual"].cpu().numpy()
+    try:
+        it_mrr = int(io["nosl"][-1])
+        assert it_mrr <= int(nosl[-1]) <= it_mrr + 9, (int(nosl[-1]), it_mrr)
+        sel = nosl[nosl <= min(50, it_mrr)]
+        np.testing.assert_allclose(res[:len(sel)], io["residual"][sel], rtol=1e-8)
+        assert oracle.true_relres(A, b, x.cpu().numpy()) < 1e-8 * (1 + 1e-6)
+    except AssertionError as e:
+        failures.append(f"[chebyshev kskipmrr k=8 rank {rank}] {e!r}"[:400])
+
     # ---- structurally nonsymmetric A (upper block triangular across the ranks): the last rank references no remote column
     # but its rows are needed by its predecessor -> a pure sender must still send / push, and must be throttled by its
     # receiver during the back-to-back basis SpMVs of the k-skip variants
