@@ -43,6 +43,9 @@ WORKLOADS = {
     "kskipmrr8_band32m": ("kskipmrr", 8, "banded", (1 << 25, 13), 46),
     "cg_band32m": ("cg", None, "banded", (1 << 25, 13), 42),
     "adaptive8_p3d512": ("adaptivekskipmrr", 8, "stencil", (512, 512, 512), 297),
+    # opt-in extensions: single-reduction CG, Chebyshev-basis k-skip MrR
+    "cgcg_p3d512": ("cgcg", None, "stencil", (512, 512, 512), 2500),
+    "cgcg_p3d256": ("cgcg", None, "stencil", (256, 256, 256), 500),
 }
 DEFAULT_WORKLOAD = "cg_p3d512"
 
@@ -75,6 +78,8 @@ def algorithmic_bytes(solver, k, n, nnz):
     b_spmv = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
     if solver == "cg":
         per_it = b_spmv + 72.0 * n
+    elif solver == "cgcg":
+        per_it = b_spmv + 80.0 * n           # p, s, x, r updated from u(=r), w: 6R 4W
     elif solver == "mrr":
         per_it = b_spmv + 80.0 * n
     elif solver == "kskipcg":
@@ -103,8 +108,8 @@ def actual_bytes(solver, k, n, nnz, matpow=False):
         return b_a + 16.0 * n + 72.0 * n
     if solver == "mrr":                                  # SpMV (A, r, Ar, y for the dots) + s-phase (3R) + update (5R 4W)
         return b_a + 24.0 * n + 24.0 * n + 72.0 * n
-    if solver == "cgcg":                                 # SpMV (A, u, w) + fused update (5R 4W, u == r without M)
-        return b_a + 16.0 * n + 72.0 * n
+    if solver == "cgcg":                                 # SpMV (A, u, w) + fused update (6R 4W, u == r without M)
+        return b_a + 16.0 * n + 80.0 * n
     first = 56.0 if solver == "kskipcg" else 72.0        # un-fused first step of a trip
     fused = 48.0 if solver == "kskipcg" else 64.0        # step fused into the SpMV epilogue: vectors read + written
     if matpow:
@@ -190,6 +195,16 @@ def cpu_solvers():
     return oracle.SOLVERS, "port", "oracle/krylov_oracle.py (port of v3/cpu; oracle/_ref not staged)"
 
 
+def cpu_solver_for(solver):
+    """(callable, kind, description) for one solver: the staged reference when it has that method (the five v3 methods),
+    else the oracle port (cgcg: the reference's sketch cannot be imported)."""
+    fns, kind, what = cpu_solvers()
+    if solver in fns:
+        return fns[solver], kind, what
+    import krylov_oracle as oracle
+    return oracle.SOLVERS[solver], "port", "oracle/krylov_oracle.py (repaired restatement; the reference file cannot be imported)"
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, timed on this box's host cores.
@@ -200,10 +215,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    solvers_cpu, cpu_kind, cpu_what = cpu_solvers()
+    solver, k, kind, dims, cap = WORKLOADS[args.workload]
+    cpu_fn, cpu_kind, cpu_what = cpu_solver_for(solver)          # also puts oracle/ on sys.path
     import host_kernels as hk
     from parallel_krylov_b200 import problems
-    solver, k, kind, dims, cap = WORKLOADS[args.workload]
+    solvers_cpu = {solver: cpu_fn}
     t0 = time.time()
     if kind == "stencil":
         rowptr, col, val, n = hk.stencil_csr(*dims)
@@ -536,7 +552,8 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only) -----------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
-        solvers_cpu, cpu_kind, cpu_what = cpu_solvers()
+        cpu_fn, cpu_kind, cpu_what = cpu_solver_for(solver)
+        solvers_cpu = {solver: cpu_fn}
         import scipy.sparse as sp
         A = sp.csr_matrix((h_val.numpy(), h_col.numpy(), h_rowptr.numpy()), shape=(n, n))
         kk = (k or 0) + 1
