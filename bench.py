@@ -44,6 +44,7 @@ WORKLOADS = {
     "cg_band32m": ("cg", None, "banded", (1 << 25, 13), 42),
     "adaptive8_p3d512": ("adaptivekskipmrr", 8, "stencil", (512, 512, 512), 297),
     # opt-in extensions: single-reduction CG, Chebyshev-basis k-skip MrR
+    "kskipmrr8_p3d512": ("kskipmrr", 8, "stencil", (512, 512, 512), 297),
     "cgcg_p3d512": ("cgcg", None, "stencil", (512, 512, 512), 2500),
     "cgcg_p3d256": ("cgcg", None, "stencil", (256, 256, 256), 500),
 }
@@ -480,14 +481,16 @@ def run_ours(args):
 
     # ---- the other BASELINE.json configs, measured briefly in the same run (default workload only) -------------------
     # N = 1: configs[1], [2], the north-star's k-skip MrR 256^3 target, CG 256^3, and configs[3], [4] on one GPU;
-    # N > 1: configs[3] (kskipmrr k=8, banded 32M) and configs[4] (adaptivekskipmrr k=8, 512^3) row-partitioned over N.
+    # N > 1: configs[3] (kskipmrr k=8, banded 32M) and configs[4] (adaptivekskipmrr k=8, 512^3) row-partitioned over N,
+    #        plus kskipmrr k=8 and the single-reduction CG (cgcg, opt-in) on the headline 512^3 system for comparison.
     other = None
     peak, peak_src = measured_peak_gbs()
     if args.workload == DEFAULT_WORKLOAD and not args.no_other:
         other = {}
         torch.cuda.empty_cache()
         names = (("mrr_p3d128", "kskipcg4_p3d256", "kskipmrr8_p3d256", "cg_p3d256", "mrr_p3d256", "kskipmrr8_band32m",
-                  "adaptive8_p3d512") if world == 1 else ("kskipmrr8_band32m", "adaptive8_p3d512"))
+                  "adaptive8_p3d512") if world == 1 else ("kskipmrr8_band32m", "adaptive8_p3d512", "kskipmrr8_p3d512",
+                                                          "cgcg_p3d512"))
         for name in names:
             s2, k2, _, _, cap2 = WORKLOADS[name]
             op2, b2, csr2, (n2, _, nnz2, _) = make_problem(name)
