@@ -143,6 +143,19 @@ int pk_spmv(pk_ctx* ctx, pk_mat* mat, double* d_x, double* d_y, double* d_x1, do
  * bandwidth (square single-GPU CSR block, rows of <= 28 nonzeros, half bandwidth bw with 640 - 2(k-1)bw >= 320);
  * PK_ERR_UNSUPPORTED otherwise (the solvers then use k two-chain SpMV passes). */
 int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1);
+/* Row-partitioned matrix powers: register copies of the neighbours' rows of A next to this block — the last `rows_above`
+ * rows of the previous rank and the first `rows_below` rows of the next one, as CSR with GLOBAL int32 column indices
+ * (device arrays, borrowed) — so that the basis of a trip needs ONE exchange of depth rows + half_bw instead of one per
+ * level (the redundant ghost-zone scheme; replaces the 2k MultiGpu.dot exchanges of v3/gpu/mpi/kskipmrr.py:55-58).
+ * row0 = global index of the first owned row, d_halo_global[h] = global index of local column n_rows + h (pk_mat_set_halo
+ * order).  Every rank must own at least rows + half_bw rows; half_bw / max_row_nnz are the GLOBAL maxima. */
+int pk_mat_set_matpow_ext(pk_mat* mat, int half_bw, int max_row_nnz, int64_t row0, int64_t n_global,
+                          const int64_t* d_halo_global, int64_t rows_above, const int32_t* d_rowptr_above,
+                          const int32_t* d_col_above, const double* d_val_above, int64_t rows_below,
+                          const int32_t* d_rowptr_below, const int32_t* d_col_below, const double* d_val_below);
+/* Longest row and half bandwidth max |global column - global row| of a CSR block given as raw device arrays
+ * (h_out[0], h_out[1]; blocking) — col holds GLOBAL indices, row0 is the global index of the block's first row. */
+int pk_csr_band_info(pk_ctx* ctx, int64_t n_rows, int64_t row0, const int32_t* d_rowptr, const int32_t* d_col, int* h_out);
 /* d_out[0] = u·v (local part; all-reduced when the context has a communicator). */
 int pk_dot(pk_ctx* ctx, int64_t n, const double* d_u, const double* d_v, double* d_out);
 /* All Gram sums of one k-skip outer trip in one pass (replaces the 6k+5 / 6k+7 cupy.dot calls,

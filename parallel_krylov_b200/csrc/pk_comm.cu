@@ -276,6 +276,30 @@ int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s) {
     return PK_OK;
 }
 
+// Neighbour exchange of the matrix-powers ghost zone (pk_matpow.cu): `depth` entries of each of the two level-0 vectors
+// to / from the previous and the next rank, one grouped send/recv on the solver's stream (graph-capturable).
+int pk_comm_ghost_exchange(pk_ctx* ctx, const double* v0, const double* v1, long long n_loc, long long depth,
+                           double* gin, bool has_prev, bool has_next) {
+    if (!ctx->comm || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
+    const int me = ctx->rank;
+    const double* src[2] = {v0, v1};
+    PK_NCCL(g_nccl.GroupStart());
+    for (int c = 0; c < 2; ++c) {
+        double* above = gin + (size_t)(2 * c + 0) * depth;
+        double* below = gin + (size_t)(2 * c + 1) * depth;
+        if (has_prev) {
+            PK_NCCL(g_nccl.Send(src[c], (size_t)depth, ncclDouble, me - 1, ctx->comm->comm, ctx->stream));
+            PK_NCCL(g_nccl.Recv(above, (size_t)depth, ncclDouble, me - 1, ctx->comm->comm, ctx->stream));
+        }
+        if (has_next) {
+            PK_NCCL(g_nccl.Send(src[c] + (n_loc - depth), (size_t)depth, ncclDouble, me + 1, ctx->comm->comm, ctx->stream));
+            PK_NCCL(g_nccl.Recv(below, (size_t)depth, ncclDouble, me + 1, ctx->comm->comm, ctx->stream));
+        }
+    }
+    PK_NCCL(g_nccl.GroupEnd());
+    return PK_OK;
+}
+
 int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s) {
     if (!ctx->comm || ctx->n_ranks <= 1) {
         if (send != recv) PK_CUDA(cudaMemcpyAsync(recv, send, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));

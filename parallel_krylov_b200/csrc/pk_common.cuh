@@ -161,6 +161,16 @@ struct pk_mat {
     bool mp_checked = false;
     int mp_rmax = 0;         // longest row
     int mp_bw = 0;           // half bandwidth max |col - row|
+    // row-partitioned matrix powers (pk_mat_set_matpow_ext): ghost rows of A from the two neighbours, level-0 ghost inputs
+    bool mp_ext = false;
+    long long mp_row0 = 0, mp_n_global = 0;
+    const long long* mp_halo_global = nullptr;                 // borrowed
+    const int32_t* mp_g_rowptr[2] = {nullptr, nullptr};        // borrowed: ghost rows above / below (global columns)
+    const int32_t* mp_g_col[2] = {nullptr, nullptr};
+    const double* mp_g_val[2] = {nullptr, nullptr};
+    long long mp_g_rows[2] = {0, 0};
+    double* mp_gin = nullptr;                                  // owned: [chain 0..1][above, below][mp_depth]
+    long long mp_depth = 0;                                    // ghost rows + bw: vector entries exchanged per side
     bool pat_on = false;
     int n_pat = 0, pat_entries = 0;
     const uint16_t* pat_id = nullptr;      // [n_rows]

@@ -60,6 +60,8 @@ int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double
 // pk_comm.cu — NCCL over NVLink
 int pk_comm_allreduce(pk_ctx* ctx, double* buf, long long n, cudaStream_t s);
 int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s);
+int pk_comm_ghost_exchange(pk_ctx* ctx, const double* v0, const double* v1, long long n_loc, long long depth, double* gin,
+                           bool has_prev, bool has_next);
 int pk_comm_halo_start(pk_ctx* ctx, pk_mat* mat, double* x, double* x1);   // pack + send/recv on the side stream
 int pk_comm_halo_wait(pk_ctx* ctx);
 void pk_mat_halo_p2p_close(pk_mat* m);                                        // main stream waits for the exchange

@@ -15,6 +15,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr int MP_T = 640;       // rows per window = threads per block (one block per SM: the rows of A fill the registers)
@@ -31,8 +33,26 @@ struct MpArgs {
     int bw;                     // half bandwidth
     int k;                      // levels to generate (dyn: the current k is read from PkState)
     int dyn;
+    // Row-partitioned operator (EXT): the block works on the WINDOW of positions that covers its owned rows, gr ghost
+    // rows of A on either side (copies of the neighbours' rows, shipped once at set-up) and bw more vector entries beyond
+    // them; position p <-> global index win0 + p.  Level 0 of the window's ghost part comes from the neighbours' vectors
+    // (depth gr + bw, exchanged ONCE per trip); levels are valid on the owned rows as long as (k-1) bw <= gr.
+    long long n_loc;            // owned rows
+    long long own_lo;           // position of the first owned row (= bw + ghost rows above)
+    long long win0;             // global index of position 0 (may be negative at the first rank)
+    long long n_global;
+    long long row0;             // global index of the first owned row
+    const long long* halo_global;   // global index of local column n_loc + h
+    const int32_t* g_rowptr[2];     // ghost rows above / below: CSR with GLOBAL column indices
+    const int32_t* g_col[2];
+    const double* g_val[2];
+    long long g_rows[2];
+    const double* gin0[2];          // level 0 of chain 0 above / below the owned rows (gr + bw entries each)
+    const double* gin1[2];
+    long long g_in[2];              // entries available above / below
 };
 
+template <bool EXT>
 __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
     if (pk_skip(ra)) return;
     const int k = a.dyn ? ra.st->k : a.k;
@@ -60,14 +80,37 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
 #pragma unroll
         for (int t = 0; t < MP_RMAX; ++t) v[t] = 0.0;
         if (row >= 0 && row < a.n) {
-            const int q0 = __ldg(a.rowptr + row);
-            cnt = __ldg(a.rowptr + row + 1) - q0;
+            // which row of A sits at this position: an owned row, a ghost row above / below (EXT), or nothing
+            const int32_t* rp = a.rowptr;
+            const int32_t* cl = a.col;
+            const double* vl = a.val;
+            long long lr = row;                                 // row index within its CSR
+            int src = 0;                                        // 0 owned (local columns), 1 ghost (global columns)
+            bool have = true;
+            if (EXT) {
+                const long long e = row - a.own_lo;             // relative to the first owned row
+                if (e >= 0 && e < a.n_loc) lr = e;
+                else if (e < 0 && -e <= a.g_rows[0]) { rp = a.g_rowptr[0]; cl = a.g_col[0]; vl = a.g_val[0]; lr = a.g_rows[0] + e; src = 1; }
+                else if (e >= a.n_loc && e - a.n_loc < a.g_rows[1]) { rp = a.g_rowptr[1]; cl = a.g_col[1]; vl = a.g_val[1]; lr = e - a.n_loc; src = 1; }
+                else have = false;
+            }
+            if (have) {
+                const int q0 = __ldg(rp + lr);
+                cnt = __ldg(rp + lr + 1) - q0;
 #pragma unroll
-            for (int t = 0; t < MP_RMAX; ++t) {
-                if (t < cnt) {
-                    v[t] = __ldg(a.val + q0 + t);
-                    const int o = __ldg(a.col + q0 + t) - (int)row;
-                    offp[t >> 2] |= ((unsigned int)(o & 0xff)) << (8 * (t & 3));
+                for (int t = 0; t < MP_RMAX; ++t) {
+                    if (t < cnt) {
+                        v[t] = __ldg(vl + q0 + t);
+                        int o;
+                        if (!EXT) o = __ldg(cl + q0 + t) - (int)row;
+                        else {
+                            const long long c = __ldg(cl + q0 + t);
+                            // global column -> offset from this row's own global index (win0 + row)
+                            const long long gc = src ? c : (c < a.n_loc ? a.row0 + c : a.halo_global[c - a.n_loc]);
+                            o = (int)(gc - (a.win0 + row));
+                        }
+                        offp[t >> 2] |= ((unsigned int)(o & 0xff)) << (8 * (t & 3));
+                    }
                 }
             }
         }
@@ -78,9 +121,18 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
         double* N1 = mp_sm + 3 * W;
         for (int i = tid; i < W; i += MP_T) {
             const long long g = s0 - bw + i;
-            const bool in = (g >= 0 && g < a.n);
-            P0[i] = in ? a.base0[g] : 0.0;
-            P1[i] = in ? a.base1[g] : 0.0;
+            double u0 = 0.0, u1 = 0.0;
+            if (g >= 0 && g < a.n) {
+                if (!EXT) { u0 = a.base0[g]; u1 = a.base1[g]; }
+                else {
+                    const long long e = g - a.own_lo;
+                    if (e >= 0 && e < a.n_loc) { u0 = a.base0[e]; u1 = a.base1[e]; }
+                    else if (e < 0 && -e <= a.g_in[0]) { u0 = a.gin0[0][a.g_in[0] + e]; u1 = a.gin1[0][a.g_in[0] + e]; }
+                    else if (e >= a.n_loc && e - a.n_loc < a.g_in[1]) { u0 = a.gin0[1][e - a.n_loc]; u1 = a.gin1[1][e - a.n_loc]; }
+                }
+            }
+            P0[i] = u0;
+            P1[i] = u1;
         }
         __syncthreads();
         for (int l = 1; l <= k; ++l) {
@@ -97,8 +149,13 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
             N0[tid + bw] = y0;
             N1[tid + bw] = y1;
             if (row >= o0 && row < o1) {
-                a.base0[(size_t)l * a.ld + row] = y0;
-                a.base1[(size_t)l * a.ld + row] = y1;
+                if (!EXT) {
+                    a.base0[(size_t)l * a.ld + row] = y0;
+                    a.base1[(size_t)l * a.ld + row] = y1;
+                } else if (row >= a.own_lo && row < a.own_lo + a.n_loc) {       // only the owned rows leave the window
+                    a.base0[(size_t)l * a.ld + (row - a.own_lo)] = y0;
+                    a.base1[(size_t)l * a.ld + (row - a.own_lo)] = y1;
+                }
             }
             __syncthreads();
             double* t0 = P0; P0 = N0; N0 = t0;
@@ -110,14 +167,15 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
     }
 }
 
-__global__ void k_band_info(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, long long n_rows, int* out) {
+__global__ void k_band_info(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, long long n_rows,
+                            long long row0, int* out) {
     int mlen = 0, mbw = 0;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
         const int q0 = rowptr[r], q1 = rowptr[r + 1];
         mlen = (q1 - q0) > mlen ? (q1 - q0) : mlen;
         if (q1 > q0) {        // sorted or not: look at both ends and, to be safe, every entry of short rows
             for (int q = q0; q < q1 && q < q0 + 64; ++q) {
-                const long long d = (long long)col[q] - r;
+                const long long d = (long long)col[q] - (r + row0);
                 const int ad = (int)(d < 0 ? -d : d) > (1 << 20) ? (1 << 20) : (int)(d < 0 ? -d : d);
                 mbw = ad > mbw ? ad : mbw;
             }
@@ -138,6 +196,29 @@ __global__ void k_band_info(const int32_t* __restrict__ rowptr, const int32_t* _
 
 }  // namespace
 
+static int band_probe(pk_ctx* ctx, const int32_t* rowptr, const int32_t* col, long long n_rows, long long row0, int* h) {
+    int* d = nullptr;
+    h[0] = h[1] = 0;
+    PK_CUDA(cudaMalloc(&d, 2 * sizeof(int)));
+    PK_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(int), ctx->stream));
+    int grid = (int)((n_rows + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_band_info<<<grid, 256, 0, ctx->stream>>>(rowptr, col, n_rows, row0, d);
+    PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return PK_OK;
+}
+
+extern "C" int pk_csr_band_info(pk_ctx* ctx, int64_t n_rows, int64_t row0, const int32_t* d_rowptr, const int32_t* d_col,
+                                int* h_out) {
+    PK_REQUIRE(ctx && h_out && (n_rows == 0 || (d_rowptr && d_col)), "null argument");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    return band_probe(ctx, d_rowptr, d_col, n_rows, row0, h_out);
+}
+
 // One-time (cached) structure probe: longest row and half bandwidth of a square, non-distributed CSR block.
 static int band_info(pk_ctx* ctx, pk_mat* m) {
     if (m->mp_checked) return PK_OK;
@@ -145,20 +226,41 @@ static int band_info(pk_ctx* ctx, pk_mat* m) {
     m->mp_rmax = 1 << 30;
     m->mp_bw = 1 << 30;
     if (m->kind == MAT_DENSE || m->distributed || !m->segs.empty() || m->rowptr == nullptr || m->n_rows != m->n_cols) return PK_OK;
-    int* d = nullptr;
     int h[2] = {0, 0};
-    PK_CUDA(cudaMalloc(&d, 2 * sizeof(int)));
-    PK_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(int), ctx->stream));
-    int grid = (int)((m->n_rows + 255) / 256);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    if (grid < 1) grid = 1;
-    k_band_info<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->n_rows, d);
-    PK_CUDA(cudaGetLastError());
-    PK_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PK_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d);
+    PK_CHECK(band_probe(ctx, m->rowptr, m->col, m->n_rows, 0, h));
     m->mp_rmax = h[0];
     m->mp_bw = h[1];
+    return PK_OK;
+}
+
+extern "C" int pk_mat_set_matpow_ext(pk_mat* m, int half_bw, int max_row_nnz, int64_t row0, int64_t n_global,
+                                     const int64_t* d_halo_global, int64_t rows_above, const int32_t* d_rowptr_above,
+                                     const int32_t* d_col_above, const double* d_val_above, int64_t rows_below,
+                                     const int32_t* d_rowptr_below, const int32_t* d_col_below, const double* d_val_below) {
+    PK_REQUIRE(m != nullptr, "null operator");
+    PK_REQUIRE(m->kind != MAT_DENSE && m->segs.empty() && m->rowptr != nullptr, "matrix powers need a CSR block with 32-bit row pointers");
+    PK_REQUIRE(half_bw >= 1 && half_bw <= 127 && max_row_nnz >= 1, "bad band description");
+    PK_REQUIRE(rows_above >= 0 && rows_below >= 0, "negative ghost row count");
+    PK_REQUIRE(rows_above == 0 || (d_rowptr_above && d_col_above && d_val_above), "null ghost rows (above)");
+    PK_REQUIRE(rows_below == 0 || (d_rowptr_below && d_col_below && d_val_below), "null ghost rows (below)");
+    PK_REQUIRE(m->n_halo == 0 || d_halo_global != nullptr, "null halo map");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    const long long depth = std::max<long long>(rows_above, rows_below) + half_bw;
+    PK_REQUIRE(m->n_rows >= depth, "block smaller than the ghost zone its neighbours need");
+    m->mp_checked = true;
+    m->mp_rmax = max_row_nnz;
+    m->mp_bw = half_bw;
+    m->mp_row0 = row0;
+    m->mp_n_global = n_global;
+    m->mp_halo_global = (const long long*)d_halo_global;
+    m->mp_g_rowptr[0] = d_rowptr_above; m->mp_g_col[0] = d_col_above; m->mp_g_val[0] = d_val_above; m->mp_g_rows[0] = rows_above;
+    m->mp_g_rowptr[1] = d_rowptr_below; m->mp_g_col[1] = d_col_below; m->mp_g_val[1] = d_val_below; m->mp_g_rows[1] = rows_below;
+    m->mp_depth = depth;
+    if (m->mp_gin) cudaFree(m->mp_gin);
+    PK_CUDA(cudaMalloc(&m->mp_gin, sizeof(double) * 4 * (size_t)depth));
+    PK_CUDA(cudaMemset(m->mp_gin, 0, sizeof(double) * 4 * (size_t)depth));
+    m->mp_ext = true;
     return PK_OK;
 }
 
@@ -171,28 +273,59 @@ bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k) {
         enabled = e ? atoi(e) : 1;
     }
     if (!enabled || k < 2) return false;
-    if (band_info(ctx, m) != PK_OK) return false;
+    if (m->distributed) {
+        // row-partitioned: needs the neighbours' ghost rows (pk_mat_set_matpow_ext), deep enough for this k, and NCCL for
+        // the once-per-trip ghost-zone exchange
+        if (!m->mp_ext || ctx->comm == nullptr) return false;
+        const long long need = (long long)(k - 1) * m->mp_bw;
+        if ((ctx->rank > 0 && m->mp_g_rows[0] < need) || (ctx->rank + 1 < ctx->n_ranks && m->mp_g_rows[1] < need)) return false;
+    } else if (band_info(ctx, m) != PK_OK) return false;
     if (m->mp_rmax > MP_RMAX || m->mp_bw > 127 || m->mp_bw < 1) return false;
     return MP_T - 2 * (k - 1) * m->mp_bw >= MP_T / 2;
 }
 
 int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn) {
-    MpArgs a;
+    MpArgs a{};
     a.rowptr = m->rowptr; a.col = m->col; a.val = m->val;
     a.n = m->n_rows; a.ld = m->ld; a.base0 = base0; a.base1 = base1;
     a.bw = m->mp_bw; a.k = k; a.dyn = dyn;
+    const bool ext = m->distributed;
+    if (ext) {
+        const bool has_prev = ctx->rank > 0, has_next = ctx->rank + 1 < ctx->n_ranks;
+        // ONE exchange per trip: depth = ghost rows + bw entries of both level-0 vectors with each neighbour
+        PK_CHECK(pk_comm_ghost_exchange(ctx, base0, base1, m->n_rows, m->mp_depth, m->mp_gin, has_prev, has_next));
+        a.n_loc = m->n_rows;
+        a.g_rows[0] = has_prev ? m->mp_g_rows[0] : 0;
+        a.g_rows[1] = has_next ? m->mp_g_rows[1] : 0;
+        a.g_in[0] = has_prev ? m->mp_depth : 0;
+        a.g_in[1] = has_next ? m->mp_depth : 0;
+        a.own_lo = a.g_in[0];
+        a.row0 = m->mp_row0;
+        a.win0 = m->mp_row0 - a.own_lo;
+        a.n_global = m->mp_n_global;
+        a.halo_global = m->mp_halo_global;
+        for (int s = 0; s < 2; ++s) {
+            a.g_rowptr[s] = m->mp_g_rowptr[s]; a.g_col[s] = m->mp_g_col[s]; a.g_val[s] = m->mp_g_val[s];
+            a.gin0[s] = m->mp_gin + (size_t)(0 + s) * m->mp_depth;
+            a.gin1[s] = m->mp_gin + (size_t)(2 + s) * m->mp_depth;
+        }
+        // the depth actually received may exceed what this k needs; rows deeper than the ghost rows only feed level 0
+        a.n = a.own_lo + a.n_loc + a.g_in[1];        // size of the window
+    }
     PkRedArgs ra{};
     ra.st = ctx->d_state;
     ra.only_rollback = ctx->ctl_only_rollback;
     ra.dyn_cj = -1;
     ra.dyn_last = 0;
     const size_t smem = sizeof(double) * 4 * (size_t)(MP_T + 2 * a.bw);
-    pk_blocks_per_sm((const void*)k_matpow, MP_T, smem);          // opts in to the dynamic shared memory size if needed
+    const void* kern = ext ? (const void*)k_matpow<true> : (const void*)k_matpow<false>;
+    pk_blocks_per_sm(kern, MP_T, smem);          // opts in to the dynamic shared memory size if needed
     const int t_out = MP_T - 2 * (k - 1) * a.bw;
     long long n_tiles = (a.n + t_out - 1) / t_out;
     int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
     if (grid < 1) grid = 1;
-    k_matpow<<<grid, MP_T, smem, ctx->stream>>>(a, ra);
+    if (ext) k_matpow<true><<<grid, MP_T, smem, ctx->stream>>>(a, ra);
+    else k_matpow<false><<<grid, MP_T, smem, ctx->stream>>>(a, ra);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         pk_set_error("matrix-powers launch: %s", cudaGetErrorString(e));

@@ -329,6 +329,7 @@ extern "C" int pk_mat_destroy(pk_mat* m) {
     if (m->d_sendbuf) cudaFree(m->d_sendbuf);
     pk_mat_halo_p2p_close(m);
     free_segs(m);
+    if (m->mp_gin) cudaFree(m->mp_gin);
     delete m;
     return PK_OK;
 }

@@ -148,7 +148,6 @@ class DistOperator(Operator):
             raise PkError(f"row blocks cover {row_offsets[-1]} rows, A has {n_global} columns")
         plan = build_halo_plan(rowptr, col_global, row_offsets, rank, group)
         col_local = plan["col_local"].contiguous()
-        del col_global
         op = cls(ctx)
         op.tensors = {"rowptr": rowptr, "col": col_local, "val": val}
         op.n_rows = n_rows
@@ -173,12 +172,64 @@ class DistOperator(Operator):
                                               ro.ctypes.data_as(C.c_void_p), _ptr(send_idx_d),
                                               C.c_void_p(send_idx_h.data_ptr()), plan["interior"][0],
                                               plan["interior"][1]), "pk_mat_set_halo")
+                op._setup_matpow(rowptr, col_global, val, plan, group, world, rank, list(row_offsets))
                 # default: halo exchange fused into the SpMV kernel over NVLink peer memory; PK_HALO=nccl keeps
                 # ncclSend/ncclRecv on a side stream (also the fallback when the peers' buffers cannot be mapped)
                 op.halo_path = "nccl"
                 if ctx.fused_allreduce and os.environ.get("PK_HALO", "p2p") != "nccl":
                     op._open_halo_push(group, world, rank, plan)
         return op
+
+    def _setup_matpow(self, rowptr, col_global, val, plan, group, world, rank, row_offsets):
+        """Row-partitioned one-pass matrix powers (csrc/pk_matpow.cu): if the GLOBAL operator has a small bandwidth (every
+        column within +-bw <= 127 of its row, rows of <= 28 nonzeros) and each rank only exchanges with its two neighbours,
+        ship copies of the neighbours' 16*bw boundary rows of A to this rank once, so that a k-skip trip needs ONE exchange
+        of depth 17*bw instead of one per basis level (redundant ghost-zone scheme).  Silently skipped otherwise."""
+        ctx = self.ctx
+        dev = ctx.torch_device
+        self.matpow_ghost_rows = 0
+        if os.environ.get("PK_MATPOW", "1") in ("0", ""):
+            return
+        n_rows, row0, n_global = self.n_rows, int(row_offsets[rank]), int(row_offsets[-1])
+        colg32 = col_global.to(torch.int32).contiguous()
+        info = (C.c_int * 2)()
+        check(ctx.lib.pk_csr_band_info(ctx.handle, n_rows, row0, _ptr(rowptr), _ptr(colg32), info), "pk_csr_band_info")
+        ro = plan["recv_off"]
+        far = any(ro[p + 1] > ro[p] and abs(p - rank) != 1 for p in range(world))
+        cdev = _comm_device(group)
+        t = torch.tensor([info[0], info[1], -n_rows, 1 if far else 0], dtype=torch.int64, device=cdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        rmax, bw, n_min, any_far = int(t[0]), int(t[1]), -int(t[2]), int(t[3])
+        if any_far or rmax > 28 or bw < 1 or bw > 127:
+            return
+        gr = min(16 * bw, (n_min - bw) // bw * bw)           # ghost rows per side; every rank must own gr + bw rows
+        if gr < bw:
+            return
+        rp64 = rowptr.to(torch.int64)
+
+        def rows_slice(lo, hi):
+            a, b = int(rp64[lo]), int(rp64[hi])
+            return ((rp64[lo:hi + 1] - a).to(torch.int32).cpu().numpy(), colg32[a:b].cpu().numpy(), val[a:b].cpu().numpy())
+
+        mine = {"top": rows_slice(0, gr), "bot": rows_slice(n_rows - gr, n_rows)}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        empty = (np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64))
+        above = everyone[rank - 1]["bot"] if rank > 0 else empty
+        below = everyone[rank + 1]["top"] if rank + 1 < world else empty
+        keep = {}
+        for tag, (rp_g, col_g, val_g) in (("above", above), ("below", below)):
+            keep[tag] = (torch.from_numpy(np.ascontiguousarray(rp_g)).to(dev), torch.from_numpy(np.ascontiguousarray(col_g)).to(dev),
+                         torch.from_numpy(np.ascontiguousarray(val_g)).to(dev))
+        halo_global = plan["halo_global"].to(dev, torch.int64).contiguous()
+        self.tensors["matpow_ghosts"] = (keep, halo_global)
+        ra = gr if rank > 0 else 0
+        rb = gr if rank + 1 < world else 0
+        check(ctx.lib.pk_mat_set_matpow_ext(self.handle, bw, rmax, row0, n_global, _ptr(halo_global),
+                                            ra, _ptr(keep["above"][0]), _ptr(keep["above"][1]), _ptr(keep["above"][2]),
+                                            rb, _ptr(keep["below"][0]), _ptr(keep["below"][1]), _ptr(keep["below"][2])),
+              "pk_mat_set_matpow_ext")
+        self.matpow_ghost_rows = gr
 
     def _open_halo_push(self, group, world, rank, plan):
         """Map the peers' halo receive buffers (CUDA IPC) so that the halo is exchanged by direct NVLink stores from

@@ -74,6 +74,35 @@ def main():
     except AssertionError as e:
         failures.append(f"[cgcg jacobi rank {rank}] {e!r}"[:400])
 
+    # ---- row-partitioned matrix powers (ghost rows of A from the neighbours, ONE exchange per trip): all k levels of both
+    # chains must equal k chained global mat-vecs bit for bit on every rank's rows
+    import ctypes as C
+    from parallel_krylov_b200._core import _ptr
+    from parallel_krylov_b200._lib import check
+    A = mats["band27"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
+    op = pkm.DistOperator.from_any_local(A[lo:hi], None)
+    if os.environ.get("PK_MATPOW", "1") not in ("0", ""):
+        k = 8
+        ld = op.ld
+        rng = np.random.default_rng(9)
+        u, v = rng.standard_normal(n), rng.standard_normal(n)
+        U = torch.zeros((k + 1) * ld, dtype=torch.float64, device="cuda")
+        V = torch.zeros((k + 1) * ld, dtype=torch.float64, device="cuda")
+        U[:hi - lo] = torch.from_numpy(u[lo:hi]).cuda()
+        V[:hi - lo] = torch.from_numpy(v[lo:hi]).cuda()
+        torch.cuda.synchronize()
+        try:
+            assert op.matpow_ghost_rows >= 7 * 13, op.matpow_ghost_rows
+            check(op.ctx.lib.pk_matpow(op.ctx.handle, op.handle, k, _ptr(U), _ptr(V)), "pk_matpow")
+            op.ctx.sync()
+            for l in range(1, k + 1):
+                u, v = A.dot(u), A.dot(v)
+                assert np.array_equal(U[l * ld:l * ld + hi - lo].cpu().numpy(), u[lo:hi]), f"chain 0 level {l}"
+                assert np.array_equal(V[l * ld:l * ld + hi - lo].cpu().numpy(), v[lo:hi]), f"chain 1 level {l}"
+        except Exception as e:
+            failures.append(f"[distributed matrix powers rank {rank}] {e!r}"[:400])
+    del op
+
     # ---- opt-in Chebyshev basis, row-partitioned: k = 8 must follow plain MrR (Gershgorin bounds all-reduced over the ranks)
     A = mats["p3d20"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
     b = problems.rhs(n, "randn", 0)
