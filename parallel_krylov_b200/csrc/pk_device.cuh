@@ -159,7 +159,18 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
     for (int j = warp; j < NS; j += NW) {
         const double* p = ra.partials + (size_t)j * ra.max_blocks;
         double v = 0.0;
-        for (int b = lane; b < nb; b += 32) v += __ldcg(p + b);
+        // the partials of up to a few thousand blocks: 4 loads in flight per lane, added in the same fixed order as a
+        // plain loop would (this serial tail of every reduction is on the critical path of each iteration: ~20 dependent
+        // L2 round trips before, 5 now)
+        int b = lane;
+        for (; b + 3 * 32 < nb; b += 4 * 32) {
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = __ldcg(p + b + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v += t[u];
+        }
+        for (; b < nb; b += 32) v += __ldcg(p + b);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
         if (lane == 0) tot[j] = v;
@@ -205,8 +216,15 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
         __syncthreads();                              // ... to the whole block
         for (int j = threadIdx.x; j < n; j += BLOCK) {
             double v = 0.0;
-            for (int p = 0; p < P; ++p)
-                v += __ldcv(pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + p)) * PK_MBOX_STRIDE + j);
+            for (int p0 = 0; p0 < P; p0 += 4) {             // four contributions requested at once ...
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    t[u] = (p0 + u < P) ? __ldcv(pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + p0 + u)) * PK_MBOX_STRIDE + j) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)                 // ... added in rank order: identical bits on every rank
+                    if (p0 + u < P) v += t[u];
+            }
             buf[j] = v;
         }
         __syncthreads();
