@@ -512,7 +512,7 @@ def run_ours(args):
                 ms2 = float(t.item())
             v_its = its2 / (ms2 * 1e-3)
             _, pib = algorithmic_bytes(s2, k2 or 0, n2, nnz2)
-            act = actual_bytes(s2, k2 or 0, n2, nnz2, one_pass_basis(name) and world == 1)
+            act = actual_bytes(s2, k2 or 0, n2, nnz2, one_pass_basis(name))
             other[name] = {"iterations_per_s": v_its, "iterations_per_solve": its2 / 2, "converged": bool(i2["converged"]),
                            "final_k": i2.get("final_k"),
                            "frac_formula": pib * v_its / 1e9 / (peak * world),

@@ -137,6 +137,14 @@ class DistOperator(Operator):
         ctx.init_comm(group)
         dev = ctx.torch_device
         rank, world = ctx.rank, ctx.n_ranks
+        prof = os.environ.get("PK_SETUP_PROF") and rank == 0       # developer switch: where does operator set-up time go
+        import time as _time
+        marks = [("start", _time.perf_counter())]
+
+        def mark(tag):
+            if prof:
+                torch.cuda.synchronize()
+                marks.append((tag, _time.perf_counter()))
         h2d = sum(t.numel() * t.element_size() for t in (rowptr, col_global, val) if not t.is_cuda)
         rowptr = rowptr.to(dev, torch.int32).contiguous()
         col_global = col_global.to(dev)
@@ -146,8 +154,10 @@ class DistOperator(Operator):
             row_offsets = row_offsets_from_local(n_rows, group) if world > 1 else [0, n_rows]
         if row_offsets[-1] != n_global:
             raise PkError(f"row blocks cover {row_offsets[-1]} rows, A has {n_global} columns")
+        mark("h2d")
         plan = build_halo_plan(rowptr, col_global, row_offsets, rank, group)
         col_local = plan["col_local"].contiguous()
+        mark("halo plan")
         op = cls(ctx)
         op.tensors = {"rowptr": rowptr, "col": col_local, "val": val}
         op.n_rows = n_rows
@@ -162,6 +172,7 @@ class DistOperator(Operator):
         with torch.cuda.device(ctx.device):
             check(ctx.lib.pk_mat_csr(ctx.handle, C.byref(op.handle), n_rows, n_rows + op.n_halo, op.nnz,
                                      _ptr(rowptr), _ptr(col_local), _ptr(val)), "pk_mat_csr")
+            mark("pk_mat_csr")
             if world > 1:
                 send_idx_d = plan["send_idx"].to(dev).contiguous()
                 send_idx_h = plan["send_idx"].cpu().contiguous()
@@ -172,12 +183,18 @@ class DistOperator(Operator):
                                               ro.ctypes.data_as(C.c_void_p), _ptr(send_idx_d),
                                               C.c_void_p(send_idx_h.data_ptr()), plan["interior"][0],
                                               plan["interior"][1]), "pk_mat_set_halo")
+                mark("set_halo")
                 op._setup_matpow(rowptr, col_global, val, plan, group, world, rank, list(row_offsets))
+                mark("matpow probe")
                 # default: halo exchange fused into the SpMV kernel over NVLink peer memory; PK_HALO=nccl keeps
                 # ncclSend/ncclRecv on a side stream (also the fallback when the peers' buffers cannot be mapped)
                 op.halo_path = "nccl"
                 if ctx.fused_allreduce and os.environ.get("PK_HALO", "p2p") != "nccl":
                     op._open_halo_push(group, world, rank, plan)
+                mark("halo push buffers (IPC)")
+        if prof:
+            print("[pk setup] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms" for a, b in zip(marks, marks[1:])),
+                  file=sys.stderr, flush=True)
         return op
 
     def _setup_matpow(self, rowptr, col_global, val, plan, group, world, rank, row_offsets):
