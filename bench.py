@@ -461,10 +461,12 @@ def run_ours(args):
     e0.record()
     it2 = 0
     h2d = 0
+    e2e_loop_s = 0.0
     for _ in range(args.steps):
         info = e2e_step()
         it2 += info["iterations"]
         h2d = info["h2d_bytes"]
+        e2e_loop_s += info["time"]
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -589,7 +591,8 @@ def run_ours(args):
         "plain_launch_iterations_per_s": plain_launch_its,
         "gpu_launches": int(launches), "spmv_launch_count": int(spmvs),
         "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_total),
-                "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1)},
+                "d2h_bytes_per_step": int(d2h_total), "ms_per_step": e2e_ms / max(args.steps, 1),
+                "solver_loop_ms_per_step": 1e3 * e2e_loop_s / max(args.steps, 1)},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "exposed_comm": exposed,
         "other_baseline_configs": other, "parity": parity,
     }

@@ -356,8 +356,11 @@ def solve_dist(method: str, comm, local_A, b, x=None, tol=1e-05, maxiter=None, k
     from .._core import solve
     if not dist.is_initialized():
         raise PkError("torch.distributed is not initialised (launch with torchrun, backend nccl)")
+    import time as _time
+    _t0 = _time.perf_counter()
     op = DistOperator.from_any_local(local_A, comm)
     ctx = op.ctx
+    _t1 = _time.perf_counter()
     n, N = op.n_rows, op.n_global
     lo = op.row0
 
@@ -376,6 +379,10 @@ def solve_dist(method: str, comm, local_A, b, x=None, tol=1e-05, maxiter=None, k
     if maxiter is None:
         maxiter = N
     x_out, info = solve(method, op, b_loc, x=x_loc, tol=tol, maxiter=maxiter, k=k, ctx=ctx, **kw)
+    if os.environ.get("PK_SETUP_PROF") and ctx.rank == 0:
+        torch.cuda.synchronize()
+        print(f"[pk solve_dist] operator {1e3 * (_t1 - _t0):.1f} ms, solve() {1e3 * (_time.perf_counter() - _t1):.1f} ms "
+              f"(loop {1e3 * info['time']:.1f} ms, pk_solve wall {1e3 * info['wall_time']:.1f} ms)", file=sys.stderr, flush=True)
     if gather_x and ctx.n_ranks > 1:
         sizes = [op.row_offsets[p + 1] - op.row_offsets[p] for p in range(ctx.n_ranks)]
         if len(set(sizes)) == 1:
