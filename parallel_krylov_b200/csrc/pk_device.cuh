@@ -97,6 +97,7 @@ struct PkRedArgs {
     // multi-GPU all-reduce fused into this kernel's last block (NVLink peer stores into per-rank mailboxes)
     const PkP2P* p2p;       // nullptr: single GPU, or NCCL path (defer = 1)
     int ar_n;               // doubles to all-reduce once the local sums are published (0: local publish only)
+    int post_only;          // 1 (with p2p): post the sums to the peers and return; k_ar_wait collects and runs the epilogue
     // Launch sequences whose shape depends on device-resident state (adaptivekskipmrr: the guard and the current k live
     // in PkState, so the host enqueues the sequence for the initial k and kernels decide for themselves):
     int only_rollback;      // 1: the kernel runs only when st->rollback != 0 (the rollback branch of a trip)
@@ -119,6 +120,60 @@ __device__ __forceinline__ bool pk_skip(const PkRedArgs& ra) {
 // temporaries (`x += alpha * p` is a multiply then an add, /root/reference/v3/cpu/cg.py:30).
 
 // pk_record / pk_stop_test / pk_epilogue (the scalar engine) live in pk_state.h: plain C++ shared with the host tests.
+
+// --------------------------------------------------------------------------------------------------------------
+// The two halves of the mailbox all-reduce (one block; called by the last block of a reducing kernel, or — the wait —
+// by the one-block kernel k_ar_wait when independent work is scheduled between post and wait).
+template <int BLOCK>
+__device__ __forceinline__ void pk_mailbox_post(const PkP2P* pp, const double* buf, int n) {
+    const int P = pp->n_ranks, me = pp->rank;
+    const unsigned long long seq = *pp->seq + 1ull;
+    const int bank = (int)(seq & 1ull);
+    for (int t = threadIdx.x; t < n * P; t += BLOCK) {
+        const int p = t / n, j = t - p * n;
+        pp->mbox[p][((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + j] = buf[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < P) {
+        pk_fence_sys();                               // release: cumulative over the block's payload stores (barrier above)
+        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
+            pp->mbox[threadIdx.x] + ((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
+        *f = seq;
+    }
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void pk_mailbox_wait(const PkP2P* pp, double* buf, int n, PkState* st) {
+    const int P = pp->n_ranks, me = pp->rank;
+    const unsigned long long seq = *pp->seq + 1ull;
+    const int bank = (int)(seq & 1ull);
+    if (threadIdx.x < P) {
+        volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(
+            pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + threadIdx.x)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
+        if (!pk_spin_until(mine, seq)) {              // a peer never arrived: stop the solve instead of hanging
+            st->done = 1;
+            st->converged = 0;
+            st->guard = -1;
+        }
+        pk_fence_sys();                               // acquire: the payload behind the flag is visible ...
+    }
+    __syncthreads();                                  // ... to the whole block
+    for (int j = threadIdx.x; j < n; j += BLOCK) {
+        double v = 0.0;
+        for (int p0 = 0; p0 < P; p0 += 4) {                 // four contributions requested at once ...
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                t[u] = (p0 + u < P) ? __ldcv(pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + p0 + u)) * PK_MBOX_STRIDE + j) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)                     // ... added in rank order: identical bits on every rank
+                if (p0 + u < P) v += t[u];
+        }
+        buf[j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *pp->seq = seq;
+}
 
 // --------------------------------------------------------------------------------------------------------------
 // Block reduction of NS running sums (fixed shape: shuffle tree, then warps in order), one partial per block,
@@ -188,47 +243,10 @@ __device__ __forceinline__ void pk_grid_reduce(double (&acc)[NS], const PkRedArg
         // contributions in RANK ORDER — so all ranks obtain bit-identical sums and take identical decisions.  Two
         // mailbox banks (sequence parity) suffice: a rank can run at most one reduction ahead of a peer.
         __syncthreads();
-        const PkP2P* pp = ra.p2p;
-        const int P = pp->n_ranks, me = pp->rank;
         double* buf = (ra.g_off >= 0) ? ra.st->gram : ra.st->red;   // Gram: the whole gram[] (all windows) is reduced
-        const int n = ra.ar_n;
-        const unsigned long long seq = *pp->seq + 1ull;
-        const int bank = (int)(seq & 1ull);
-        for (int t = threadIdx.x; t < n * P; t += BLOCK) {
-            const int p = t / n, j = t - p * n;
-            pp->mbox[p][((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + j] = buf[j];
-        }
-        __syncthreads();
-        if (threadIdx.x < P) {
-            pk_fence_sys();                           // release: cumulative over the block's payload stores (barrier above)
-            volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
-                pp->mbox[threadIdx.x] + ((size_t)(bank * PK_MAX_RANKS + me)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
-            *f = seq;
-            volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(
-                pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + threadIdx.x)) * PK_MBOX_STRIDE + PK_MBOX_PAYLOAD);
-            if (!pk_spin_until(mine, seq)) {          // a peer never arrived: stop the solve instead of hanging
-                ra.st->done = 1;
-                ra.st->converged = 0;
-                ra.st->guard = -1;
-            }
-            pk_fence_sys();                           // acquire: the payload behind the flag is visible ...
-        }
-        __syncthreads();                              // ... to the whole block
-        for (int j = threadIdx.x; j < n; j += BLOCK) {
-            double v = 0.0;
-            for (int p0 = 0; p0 < P; p0 += 4) {             // four contributions requested at once ...
-                double t[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    t[u] = (p0 + u < P) ? __ldcv(pp->mbox[me] + ((size_t)(bank * PK_MAX_RANKS + p0 + u)) * PK_MBOX_STRIDE + j) : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)                 // ... added in rank order: identical bits on every rank
-                    if (p0 + u < P) v += t[u];
-            }
-            buf[j] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *pp->seq = seq;
+        pk_mailbox_post<BLOCK>(ra.p2p, buf, ra.ar_n);
+        if (ra.post_only) return;           // a later kernel (k_ar_wait) collects: the flight overlaps the work in between
+        pk_mailbox_wait<BLOCK>(ra.p2p, buf, ra.ar_n, ra.st);
     }
     if (threadIdx.x == 0 && !ra.defer) pk_epilogue<GRAM>(ra.epi, ra.st);
 }

@@ -59,6 +59,37 @@ __global__ void __launch_bounds__(EW_BLOCK) k_cg_xr(long long n, double* __restr
     pk_grid_reduce<1, EW_BLOCK>(acc, ra);
 }
 
+// ---- CG with the x-update hiding the r.r all-reduce (multi-GPU): r -= alpha v ; r.r is POSTED to the peers by the last
+//      block; x += alpha p runs while the sums are in flight; a one-block kernel collects them and runs the epilogue.
+//      Same arithmetic per element as k_cg_xr (cg.py:30-33), two launches more, one all-reduce latency less.
+__global__ void __launch_bounds__(EW_BLOCK) k_cg_r(long long n, double* __restrict__ r, const double* __restrict__ v,
+                                                   PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    const double alpha = ra.st->alpha;
+    double acc[1] = {0.0};
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) {
+        double ri = r[i] - alpha * v[i];
+        r[i] = ri;
+        acc[0] += ri * ri;
+    }
+    pk_grid_reduce<1, EW_BLOCK>(acc, ra);
+}
+
+__global__ void __launch_bounds__(EW_BLOCK) k_cg_x(long long n, double* __restrict__ x, const double* __restrict__ p,
+                                                   const PkState* st) {
+    if (pk_done(st)) return;
+    const double alpha = st->alpha;
+    const long long stride = (long long)gridDim.x * EW_BLOCK;
+    for (long long i = (long long)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += stride) x[i] = x[i] + alpha * p[i];
+}
+
+__global__ void __launch_bounds__(64) k_ar_wait(const PkP2P* pp, PkState* st, int n, int epi) {
+    if (pk_done(st)) return;
+    pk_mailbox_wait<64>(pp, st->red, n, st);
+    if (threadIdx.x == 0) pk_epilogue<false>(epi, st);
+}
+
 // ---- CG: p = r + beta p  — v3/cpu/cg.py:35 -----------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_BLOCK) k_cg_p(long long n, double* __restrict__ p, const double* __restrict__ r,
                                                    const PkState* st) {
@@ -463,6 +494,7 @@ inline PkRedArgs red_args(pk_ctx* ctx, int epi, int g_off = -1) {
     ra.store_only = 0;
     ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;
     ra.ar_n = 0;          // set by the launcher: number of sums this kernel all-reduces
+    ra.post_only = 0;
     ra.only_rollback = ctx->ctl_only_rollback;
     ra.dyn_cj = ctx->ctl_dyn_cj;
     ra.dyn_last = ctx->ctl_dyn_last;
@@ -556,6 +588,29 @@ int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double
     k_cg_xr<<<ew_grid(ctx, k_cg_xr, n), EW_BLOCK, 0, ctx->stream>>>(n, x, r, p, v, red_args_n(ctx, EPI_CG_BETA, 1));
     PK_LAUNCH_CHECK();
     return pk_finish_reduce(ctx, 1, EPI_CG_BETA, -1, 0);
+}
+
+// x += alpha p ; r -= alpha v ; r.r all-reduced ; beta, residual, stop test — with the all-reduce's flight hidden behind the
+// x-update when the dots go through the NVLink mailboxes (PK_CG_SPLIT=0 keeps the single kernel)
+int pk_launch_cg_xr_split(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v) {
+    static int split = -1;
+    if (split < 0) {
+        const char* e = getenv("PK_CG_SPLIT");
+        split = e ? atoi(e) : 1;
+    }
+    if (!split || ctx->n_ranks <= 1 || !ctx->d_p2p) return pk_launch_cg_xr(ctx, n, x, r, p, v);
+    PkRedArgs ra = red_args_n(ctx, EPI_CG_BETA, 1);
+    ra.post_only = 1;
+    if (ra.p2p == nullptr) ra.post_only = 0;             // nocomm (compute-only timing): the epilogue runs in k_cg_r
+    k_cg_r<<<ew_grid(ctx, k_cg_r, n), EW_BLOCK, 0, ctx->stream>>>(n, r, v, ra);
+    PK_LAUNCH_CHECK();
+    k_cg_x<<<ew_grid(ctx, k_cg_x, n), EW_BLOCK, 0, ctx->stream>>>(n, x, p, ctx->d_state);
+    PK_LAUNCH_CHECK();
+    if (ra.post_only) {
+        k_ar_wait<<<1, 64, 0, ctx->stream>>>(ctx->d_p2p, ctx->d_state, 1, EPI_CG_BETA);
+        PK_LAUNCH_CHECK();
+    }
+    return PK_OK;
 }
 
 int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r) {

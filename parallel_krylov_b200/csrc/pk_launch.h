@@ -13,6 +13,7 @@ int pk_finish_reduce(pk_ctx* ctx, int nsums, int epi, int g_off, int ignore_done
 int pk_launch_dot(pk_ctx* ctx, long long n, const double* u, const double* v, int epi, int ignore_done);
 int pk_launch_resid_init(pk_ctx* ctx, long long n, const double* b, const double* v, double* r, double* p, int epi);
 int pk_launch_cg_xr(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v);
+int pk_launch_cg_xr_split(pk_ctx* ctx, long long n, double* x, double* r, const double* p, const double* v);
 int pk_launch_cg_p(pk_ctx* ctx, long long n, double* p, const double* r);
 int pk_launch_mrr_first(pk_ctx* ctx, long long n, const double* ar, double* r, double* x, double* y, double* z,
                         int epi);

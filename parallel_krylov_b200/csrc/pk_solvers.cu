@@ -597,7 +597,7 @@ struct Solve {
         }
         PK_CHECK(run_batches(1, 0, [&]() -> int {
             PK_CHECK(apply(p, v, p, EPI_CG_ALPHA));               // v = A p ; sigma = p.v ; alpha
-            PK_CHECK(pk_launch_cg_xr(ctx, n, x, r, p, v));        // x += alpha p ; r -= alpha v ; gamma' ; beta ; test
+            PK_CHECK(pk_launch_cg_xr_split(ctx, n, x, r, p, v));  // x += alpha p ; r -= alpha v ; gamma' ; beta ; test
             PK_CHECK(pk_launch_cg_p(ctx, n, p, r));               // p = r + beta p
             return PK_OK;
         }));

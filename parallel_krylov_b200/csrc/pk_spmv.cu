@@ -1334,6 +1334,7 @@ static int spmv_impl(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, d
     ra.ar_n = dots.w ? 3 + dots.extra_sums : (((dots.fuse == 1 || dots.fuse == 2) && dots.epi != EPI_KS_STEP) ? 1 : 0);
     ra.g_off = -1;
     ra.red_off = 0;
+    ra.post_only = 0;
     ra.block_off = 0;
     ra.nb_total = 0;
     ra.store_only = 0;
