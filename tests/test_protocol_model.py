@@ -58,6 +58,58 @@ def test_mailbox_allreduce_two_banks_suffice(P):
             assert results[r] == want
 
 
+def _allreduce_split_rank(me, P, mbox, n_rounds, values, results):
+    """CG's r.r reduction with post and wait in DIFFERENT kernels (k_cg_r posts, k_cg_x runs, k_ar_wait collects),
+    alternating with the ordinary post+wait reduction of the SpMV epilogue, as in Solve::cg() on several GPUs."""
+    for seq in range(1, n_rounds + 1):
+        bank = seq & 1
+        v = values[me][seq]
+        for p in range(P):
+            mbox[p][bank][me]["payload"] = (seq, v)
+            yield
+        for p in range(P):
+            mbox[p][bank][me]["flag"] = seq
+            yield
+        if seq % 2 == 0:                            # the split reduction: independent work between post and wait
+            for _ in range(5):
+                yield
+        for p in range(P):
+            while mbox[me][bank][p]["flag"] != seq:
+                yield
+        total = 0
+        for p in range(P):
+            s, val = mbox[me][bank][p]["payload"]
+            assert s == seq, f"rank {me} read payload of seq {s} while reducing seq {seq}"
+            total += val
+            yield
+        results[me].append(total)
+
+
+@pytest.mark.parametrize("P", [2, 8])
+def test_split_post_wait_allreduce_keeps_the_two_bank_invariant(P):
+    rng = random.Random(50 + P)
+    for trial in range(200):
+        n_rounds = 12
+        values = [[rng.randrange(1000) for _ in range(n_rounds + 1)] for _ in range(P)]
+        mbox = [[[{"payload": (0, 0), "flag": 0} for _ in range(P)] for _ in range(2)] for _ in range(P)]
+        results = [[] for _ in range(P)]
+        gens = [_allreduce_split_rank(r, P, mbox, n_rounds, values, results) for r in range(P)]
+        alive = list(range(P))
+        fav = rng.randrange(P)
+        steps = 0
+        while alive:
+            r = fav if (fav in alive and rng.random() < 0.7) else rng.choice(alive)
+            try:
+                next(gens[r])
+            except StopIteration:
+                alive.remove(r)
+            steps += 1
+            assert steps < 2_000_000, "deadlock in the model"
+        want = [sum(values[p][s] for p in range(P)) for s in range(1, n_rounds + 1)]
+        for r in range(P):
+            assert results[r] == want
+
+
 def _halo_rank(me, P, recv, n_rounds, data, got, sends, symmetric_flags=True):
     """One rank's SpMV kernels with the exchange fused in (csrc/pk_spmv.cu: k_spmv_tma<HALO>): at its start the kernel
     pushes my entries to the ranks that need them and then raises its flag at EVERY peer (any rank it exchanges with in
