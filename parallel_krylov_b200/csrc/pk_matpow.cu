@@ -61,9 +61,10 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
     const int ghost = (k - 1) * bw;
     const int t_out = MP_T - 2 * ghost;                 // finished rows per window (host guarantees >= MP_T / 2 for a.k)
     const int W = MP_T + 2 * bw;                        // a level in shared memory: the window + bw entries on either side
-    extern __shared__ __align__(16) double mp_sm[];     // [chain 0..1][buffer 0..1][W]
+    // the two chains are interleaved (one double2 per position): a gather is ONE 128-bit shared load for both chains
+    extern __shared__ __align__(16) double2 mp_sm[];    // [buffer 0..1][W]
     const int tid = threadIdx.x;
-    for (int i = tid; i < 4 * W; i += MP_T) mp_sm[i] = 0.0;     // pads of the buffers levels >= 1 are written into
+    for (int i = tid; i < 2 * W; i += MP_T) mp_sm[i] = make_double2(0.0, 0.0);   // pads of the buffer levels >= 1 are written into
     __syncthreads();
     const long long n_tiles = (a.n + t_out - 1) / t_out;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -115,10 +116,8 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
             }
         }
         // ---- level 0 of both chains -> shared memory (window + bw on either side; zeros outside the matrix)
-        double* P0 = mp_sm;
-        double* N0 = mp_sm + W;
-        double* P1 = mp_sm + 2 * W;
-        double* N1 = mp_sm + 3 * W;
+        double2* P = mp_sm;
+        double2* N = mp_sm + W;
         for (int i = tid; i < W; i += MP_T) {
             const long long g = s0 - bw + i;
             double u0 = 0.0, u1 = 0.0;
@@ -131,8 +130,7 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
                     else if (e >= a.n_loc && e - a.n_loc < a.g_in[1]) { u0 = a.gin0[1][e - a.n_loc]; u1 = a.gin1[1][e - a.n_loc]; }
                 }
             }
-            P0[i] = u0;
-            P1[i] = u1;
+            P[i] = make_double2(u0, u1);
         }
         __syncthreads();
         for (int l = 1; l <= k; ++l) {
@@ -141,13 +139,12 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
             for (int t = 0; t < MP_RMAX; ++t) {
                 if (t < cnt) {                           // left to right over the CSR entries of the row
                     const int o = (int)(signed char)((offp[t >> 2] >> (8 * (t & 3))) & 0xffu);
-                    const int idx = tid + bw + o;
-                    y0 += v[t] * P0[idx];
-                    y1 += v[t] * P1[idx];
+                    const double2 pv = P[tid + bw + o];
+                    y0 += v[t] * pv.x;
+                    y1 += v[t] * pv.y;
                 }
             }
-            N0[tid + bw] = y0;
-            N1[tid + bw] = y1;
+            N[tid + bw] = make_double2(y0, y1);
             if (row >= o0 && row < o1) {
                 if (!EXT) {
                     a.base0[(size_t)l * a.ld + row] = y0;
@@ -158,8 +155,7 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
                 }
             }
             __syncthreads();
-            double* t0 = P0; P0 = N0; N0 = t0;
-            double* t1 = P1; P1 = N1; N1 = t1;
+            double2* t0 = P; P = N; N = t0;
         }
         // the buffer that held level 0 carried real neighbour data in its pads; levels >= 1 of the next window must not see
         // stale pads of a different window as anything but finite numbers — they are finite, and only ever feed rows outside
