@@ -177,7 +177,7 @@ typedef struct {
     int32_t x_is_zero;     /* 1: x0 == 0, skip the initial A·x (result identical: b - A·0 == b)                   */
     int64_t global_n;      /* global number of rows (== n_rows when not distributed)                             */
     const double* d_mdiag; /* PK_CGCG only: diagonal of the Jacobi preconditioner M (local rows), u = r / M; NULL = none  */
-    int32_t basis;         /* PK_KSKIPMRR only: 0 = the reference's monomial basis A^j r (default, parity path);
+    int32_t basis;         /* PK_KSKIPCG / PK_KSKIPMRR: 0 = the reference's monomial basis A^j r (default, parity path);
                               1 = Chebyshev basis T_j((A - d)/c) r on [lam_lo, lam_hi] (opt-in)         */
     int32_t pad0;
     double lam_lo, lam_hi; /* basis = 1: bounds of the spectrum of A (pk_mat_gershgorin gives rigorous ones)                */

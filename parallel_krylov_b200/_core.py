@@ -425,14 +425,14 @@ def solve(method: str, A, b, x=None, tol=1e-05, maxiter=None, k=0, *, check_ever
             if mt.numel() != n:
                 raise PkError(f"M has {mt.numel()} entries; expected the diagonal for {n} local rows")
             mdiag = mt.to(device=dev, dtype=torch.float64).contiguous()
-    # Basis of the k-skip trips (kskipmrr): None / "monomial" = the reference's A^j r (parity path, default);
+    # Basis of the k-skip trips (kskipmrr, kskipcg): None / "monomial" = the reference's A^j r (parity path, default);
     # "chebyshev" = T_j((A - d)/c) r on Gershgorin bounds of the spectrum, or ("chebyshev", lam_lo, lam_hi) with bounds
     # of the caller's — numerically safe at k = 8, 12, 16 where the monomial basis is not (opt-in).
     basis_id, lam_lo, lam_hi = 0, 0.0, 0.0
     if basis is not None and basis != "monomial":
         name = basis if isinstance(basis, str) else basis[0]
-        if name != "chebyshev" or method != "kskipmrr":
-            raise PkError(f"basis={basis!r}: only 'chebyshev' for kskipmrr (or None / 'monomial')")
+        if name != "chebyshev" or method not in ("kskipmrr", "kskipcg"):
+            raise PkError(f"basis={basis!r}: only 'chebyshev', for kskipmrr / kskipcg (or None / 'monomial')")
         basis_id = 1
         if isinstance(basis, str):
             bounds = (C.c_double * 2)()

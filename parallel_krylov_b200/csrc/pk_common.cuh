@@ -83,9 +83,6 @@ struct pk_ctx {
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
-    // PK_PROF_DETAIL=1: event marks between the sub-launches of a distributed operator application (stderr report)
-    bool prof_detail = false;
-    std::vector<std::pair<cudaEvent_t, int>> seg_ev;
 };
 
 // Halo exchange by direct NVLink stores, fused into the operator kernel (no NCCL on the data path): at its start the

@@ -138,3 +138,38 @@ PK_HD inline void pk_kskipmrr_coef_cheb(const double* G, int k, double c, double
         Ld -= 2;                                    // al keeps Ld + 2, be Ld + 1, de Ld valid entries
     }
 }
+
+// k-skip CG on the Chebyshev basis: U_j = T_j(Ah) r (j <= k), V_j = T_j(Ah) p (j <= k+1); moments a_l = (r, T_l r),
+// f_l = (p, T_l p), c_l = (r, T_l p) from the same six Gram sums per level (CG layout of pk_gram); the reference's step
+// recurrences (/root/reference/v3/cpu/kskipcg.py:51-52, :59-68) with f[l+1], f[l+2], c[l+1] replaced by (A f)_l, (A^2 f)_l,
+// (A c)_l.  Same iterates as CG in exact arithmetic; follows plain CG to ~1e-12 at k = 8, 12 in fp64.
+PK_HD inline void pk_kskipcg_coef_cheb(const double* G, int k, double c, double d, double* coef) {
+    double a[2 * PK_KMAX + 1], f[2 * PK_KMAX + 3], cc[2 * PK_KMAX + 2];
+    double Af[2 * PK_KMAX + 3], AAf[2 * PK_KMAX + 3], Ac[2 * PK_KMAX + 2];
+    a[0] = G[0];
+    if (k >= 1) a[1] = G[1];
+    for (int j = 2; j < 2 * k + 1; ++j) a[j] = 2.0 * G[6 * (j >> 1) + (j & 1)] - a[j & 1];
+    cc[0] = G[2];                          // U0.V0
+    cc[1] = G[3];                          // U0.V1
+    for (int j = 2; j < 2 * k + 2; ++j) cc[j] = 2.0 * G[6 * (j >> 1) + 2 + (j & 1)] - cc[j & 1];
+    f[0] = G[4];                           // V0.V0
+    f[1] = G[5];                           // V0.V1
+    for (int j = 2; j < 2 * k + 3; ++j) f[j] = 2.0 * G[6 * (j >> 1) + 4 + (j & 1)] - f[j & 1];
+    for (int j = 0; j <= k; ++j) {
+        const int L = 2 * (k - j) + 1;     // entries the recurrence updates at this step; f has L + 2, cc L + 1, a L valid
+        pk_cheb_mulA(f, L + 1, c, d, Af);
+        pk_cheb_mulA(Af, L, c, d, AAf);
+        pk_cheb_mulA(cc, L, c, d, Ac);
+        const double alpha = a[0] / Af[0];                               // kskipcg.py:51 / :67
+        const double beta = (PK_SQ(alpha) * AAf[0]) / a[0] - 1.0;        // :52 / :68
+        coef[2 * j] = alpha;
+        coef[2 * j + 1] = beta;
+        if (j == k) break;
+        for (int l = 0; l < L; ++l) {                                     // :60-64
+            a[l] = a[l] + alpha * (alpha * AAf[l] - 2.0 * Ac[l]);
+            const double dd = cc[l] - alpha * Af[l];
+            cc[l] = a[l] + dd * beta;
+            f[l] = cc[l] + beta * (dd + beta * f[l]);
+        }
+    }
+}

@@ -114,7 +114,6 @@ extern "C" int pk_prof_begin(pk_ctx* c, int max_launches) {
     }
     c->prof_used = 0;
     c->prof_on = true;
-    c->prof_detail = getenv("PK_PROF_DETAIL") != nullptr;
     return PK_OK;
 }
 
@@ -126,22 +125,6 @@ extern "C" int pk_prof_end(pk_ctx* c, double* total_ms, int64_t* n_launches) {
         float ms = 0.f;
         PK_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
         tot += ms;
-    }
-    if (c->prof_detail && !c->seg_ev.empty()) {
-        double seg[4] = {0, 0, 0, 0};
-        long long cnt[4] = {0, 0, 0, 0};
-        for (size_t i = 0; i + 1 < c->seg_ev.size(); ++i) {
-            const int t0 = c->seg_ev[i].second, t1 = c->seg_ev[i + 1].second;
-            if (t1 == t0 + 1) {
-                float ms = 0.f;
-                if (cudaEventElapsedTime(&ms, c->seg_ev[i].first, c->seg_ev[i + 1].first) == cudaSuccess) { seg[t0] += ms; cnt[t0]++; }
-            }
-        }
-        fprintf(stderr, "[pk prof rank %d] push %.1f us, interior %.1f us, boundary %.1f us (avg over %lld applications)\n",
-                c->rank, cnt[0] ? 1e3 * seg[0] / cnt[0] : 0.0, cnt[1] ? 1e3 * seg[1] / cnt[1] : 0.0,
-                cnt[2] ? 1e3 * seg[2] / cnt[2] : 0.0, cnt[0]);
-        for (auto& pr : c->seg_ev) cudaEventDestroy(pr.first);
-        c->seg_ev.clear();
     }
     if (total_ms) *total_ms = tot;
     if (n_launches) *n_launches = (int64_t)(c->prof_used / 2);
@@ -435,7 +418,7 @@ extern "C" int64_t pk_work_doubles(int method, int64_t ld, int k) {
     switch (method) {
         case PK_CG: nvec = 3; break;                       // r, p, v
         case PK_MRR: nvec = 4; break;                      // r, Ar, y, z
-        case PK_KSKIPCG: nvec = (k + 1) + (k + 2) + 1; break;  // Ar[0..k], Ap[0..k+1], spare Ap0 (fused steps)
+        case PK_KSKIPCG: nvec = (k + 1) + (k + 2) + 2; break;  // Ar[0..k], Ap[0..k+1], spare Ap0 (fused steps), A p (Chebyshev basis)
         case PK_KSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;          // Ar[0..k+1], Ay[0..k], z, spare Ar0, A r (Chebyshev basis)
         case PK_ADAPTIVEKSKIPMRR: nvec = (k + 2) + (k + 1) + 3; break;  // + best_x
         case PK_CGCG: nvec = 5; break;                     // r, w, p, s, u (u aliases r without a preconditioner)
@@ -658,8 +641,56 @@ struct Solve {
     }
 
     // ---- k-skip CG: /root/reference/v3/cpu/kskipcg.py:8-87 ---------------------------------------------------
+    // ---- k-skip CG on a Chebyshev basis (opt-in; pk_scalars.h: pk_kskipcg_coef_cheb) — the mirror image of
+    // kskipmrr_chebyshev(): U_j = T_j(Ah) r in the Ar rows, V_j = T_j(Ah) p in the Ap rows, A p in its own vector.
+    int kskipcg_chebyshev() {
+        const int k = o.k;
+        PK_REQUIRE(o.lam_hi > o.lam_lo, "Chebyshev basis needs spectrum bounds lam_lo < lam_hi (pk_mat_gershgorin)");
+        PK_REQUIRE(A->kind != MAT_DENSE && A->use_tma && !A->pat_on,
+                   "the Chebyshev basis needs the TMA CSR kernel (16-byte aligned CSR arrays, no pattern compression)");
+        const double c = 0.5 * (o.lam_hi - o.lam_lo), d = 0.5 * (o.lam_hi + o.lam_lo);
+        auto U = [&](int j) { return vec(j); };                   // rows 0..k,   U(0) = r
+        auto V = [&](int j) { return vec(k + 1 + j); };           // rows 0..k+1, V(0) = p
+        double *spare = vec(2 * k + 3), *AP = vec(2 * k + 4);
+        {
+            PkState* h = ctx->h_state;
+            h->cheb_c = c;
+            h->cheb_d = d;
+            PK_CUDA(cudaMemcpyAsync(&ctx->d_state->cheb_c, &h->cheb_c, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        PK_CHECK(initial_residual(U(0), V(0), AP, EPI_CG_INIT));
+        PK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        PK_CHECK(apply(V(0), AP));                                // invariant: AP = A p at trip start
+        PK_CHECK(run_batches(k + 1, 0, [&]() -> int {
+            PK_CHECK(pk_launch_axpby(ctx, n, 1.0 / c, AP, -d / c, V(0), V(1)));        // V_1 = (A p - d p) / c
+            for (int j = 1; j <= k; ++j) {                        // (U_j, V_{j+1}) from (U_{j-1}, V_j) and the levels before
+                PkDots dd;
+                dd.fuse = 3;
+                if (j == 1) { dd.cs[0] = 1.0 / c; dd.cs[1] = -d / c; dd.cs[2] = 0.0; dd.f_a = nullptr; }
+                else { dd.cs[0] = 2.0 / c; dd.cs[1] = -2.0 * d / c; dd.cs[2] = -1.0; dd.f_a = U(j - 2); }
+                dd.cs[3] = 2.0 / c; dd.cs[4] = -2.0 * d / c; dd.cs[5] = -1.0;
+                dd.f_b = V(j - 1);
+                PK_CHECK(pk_launch_spmv(ctx, A, U(j - 1), U(j), V(j), V(j + 1), dd));
+            }
+            PK_CHECK(pk_launch_gram(ctx, 1, n, ld, U(0), k + 1, V(0), k + 2, k + 2, EPI_GRAM_CG_CHEB));
+            double* cur = (k % 2 == 1) ? spare : V(0);
+            PK_CHECK(pk_launch_kscg_update(ctx, n, x, U(0), V(0), cur, AP, 0, k == 0 ? EPI_KS_TRIP_END : EPI_KS_STEP));
+            for (int j = 1; j <= k; ++j) {
+                double* nxt = (cur == spare) ? V(0) : spare;
+                PkDots ds;
+                ds.epi = (j == k) ? EPI_KS_TRIP_END : EPI_KS_STEP;
+                ds.fuse = 2; ds.cj = j; ds.f_a = U(0); ds.f_x = x; ds.f_out = nxt;
+                PK_CHECK(pk_launch_spmv(ctx, A, cur, nullptr, nullptr, nullptr, ds));
+                cur = nxt;
+            }
+            return apply(V(0), AP);                               // cur == V(0): A p for the next trip
+        }));
+        return PK_OK;
+    }
+
     int kskipcg() {
         const int k = o.k;
+        if (o.basis == 1) return kskipcg_chebyshev();
         auto Ar = [&](int j) { return vec(j); };                  // rows 0..k
         auto Ap = [&](int j) { return vec(k + 1 + j); };          // rows 0..k+1
         double* spare = vec(2 * k + 3);                           // second home of Ap[0] for the fused steps

@@ -22,8 +22,6 @@
 
 namespace {
 
-__device__ __forceinline__ bool pk_done(const PkState* st) { return *((volatile const int*)&st->done) != 0; }
-
 struct SpmvArgs {
     const int32_t* rowptr;
     const int32_t* col;
@@ -1295,14 +1293,6 @@ extern "C" int pk_mat_set_patterns(pk_mat* m, int n_pat, int n_entries, const ui
     m->n_pat = n_pat; m->pat_entries = n_entries;
     m->pat_on = true;
     return PK_OK;
-}
-
-static void seg_mark(pk_ctx* ctx, int tag) {
-    if (!ctx->prof_detail || !ctx->prof_on || ctx->seg_ev.size() > 60000) return;
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, ctx->stream);
-    ctx->seg_ev.push_back({e, tag});
 }
 
 int pk_launch_spmv(pk_ctx* ctx, pk_mat* m, double* x, double* y, double* x1, double* y1, PkDots dots) {

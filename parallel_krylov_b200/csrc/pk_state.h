@@ -71,6 +71,7 @@ enum PkEpi : int {
     EPI_CGCG_INIT,       // red[0] = u.w, red[3] = r.u          -> gamma, alpha = gamma/delta, beta = 0
     EPI_CGCG,            // red[0] = u.w, red[3] = r.u, red[4] = r.r -> it++, res[it], stop test, beta, alpha (one reduction/iteration)
     EPI_GRAM_MRR_CHEB,   // gram[] of the Chebyshev basis complete -> coef[] = (zeta_j, eta_j)
+    EPI_GRAM_CG_CHEB,    // gram[] of the Chebyshev basis complete -> coef[] = (alpha_j, beta_j)
 };
 
 
@@ -253,6 +254,9 @@ PK_HD inline void pk_epilogue(int epi, PkState* st) {
             break;
         case EPI_GRAM_MRR_CHEB:
             if (GRAM) pk_kskipmrr_coef_cheb(st->gram, st->k, st->cheb_c, st->cheb_d, st->coef);
+            break;
+        case EPI_GRAM_CG_CHEB:
+            if (GRAM) pk_kskipcg_coef_cheb(st->gram, st->k, st->cheb_c, st->cheb_d, st->coef);
             break;
         default:
             break;

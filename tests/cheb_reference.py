@@ -115,3 +115,88 @@ def kskipmrr_chebyshev(A, b, tol=1e-8, maxiter=None, k=8, bounds=None, coef_fn=c
         it += k + 1
         res.append(norm(r) / bn); nosl.append(it)
     return x, {"residual": np.array(res), "nosl": np.array(nosl), "converged": converged}
+
+
+# ---- k-skip CG on the Chebyshev basis (mirror of the MrR variant; pk_scalars.h: pk_kskipcg_coef_cheb) ------------------
+def coefficients_cg(G, k, c, d):
+    """(alpha_j, beta_j), j = 0..k, from the Gram sums of the Chebyshev basis (layout of pk_gram, CG mode)."""
+    a = np.zeros(2 * k + 1); f = np.zeros(2 * k + 3); cc = np.zeros(2 * k + 2)
+    a[0] = G[0]
+    if k >= 1:
+        a[1] = G[1]
+    for j in range(2, 2 * k + 1):
+        a[j] = 2.0 * G[6 * (j >> 1) + (j & 1)] - a[j & 1]
+    cc[0], cc[1] = G[2], G[3]
+    for j in range(2, 2 * k + 2):
+        cc[j] = 2.0 * G[6 * (j >> 1) + 2 + (j & 1)] - cc[j & 1]
+    f[0], f[1] = G[4], G[5]
+    for j in range(2, 2 * k + 3):
+        f[j] = 2.0 * G[6 * (j >> 1) + 4 + (j & 1)] - f[j & 1]
+    coef = np.zeros(2 * (k + 1))
+    for j in range(k + 1):
+        L = 2 * (k - j) + 1
+        Af = mul_a(f, L + 1, c, d)
+        AAf = mul_a(Af, L, c, d)
+        Ac = mul_a(cc, L, c, d)
+        alpha = a[0] / Af[0]
+        beta = ((alpha * alpha) * AAf[0]) / a[0] - 1.0
+        coef[2 * j], coef[2 * j + 1] = alpha, beta
+        if j == k:
+            break
+        for l in range(L):
+            a[l] = a[l] + alpha * (alpha * AAf[l] - 2.0 * Ac[l])
+            dd = cc[l] - alpha * Af[l]
+            cc[l] = a[l] + dd * beta
+            f[l] = cc[l] + beta * (dd + beta * f[l])
+    return coef
+
+
+def gram_layout_cg(U, V, k):
+    G = np.zeros(6 * (k + 2))
+    row = lambda M, j: M[j] if j < M.shape[0] else None
+    dt = lambda a, b: 0.0 if a is None or b is None else float(dot(a, b))
+    for jj in range(k + 2):
+        u0, u1, v0, v1 = row(U, jj), row(U, jj + 1), row(V, jj), row(V, jj + 1)
+        G[6 * jj:6 * jj + 6] = [dt(u0, u0), dt(u0, u1), dt(u0, v0), dt(u0, v1), dt(v0, v0), dt(v0, v1)]
+    return G
+
+
+def kskipcg_chebyshev(A, b, tol=1e-8, maxiter=None, k=8, bounds=None, coef_fn=coefficients_cg):
+    """Launch order of Solve::kskipcg_chebyshev with numpy standing in for the vector kernels."""
+    n = b.size
+    maxiter = n if maxiter is None else maxiter
+    x = np.zeros(n)
+    bn = norm(b)
+    lo, hi = bounds if bounds is not None else gershgorin(A)
+    c, d = 0.5 * (hi - lo), 0.5 * (hi + lo)
+    r = b - A.dot(x)
+    p = r.copy()
+    AP = A.dot(p)
+    U = np.zeros((k + 1, n)); V = np.zeros((k + 2, n))
+    res, nosl, it = [], [0], 0
+    converged = False
+    while it < maxiter:
+        res.append(norm(r) / bn)
+        if res[-1] < tol:
+            converged = True
+            break
+        U[0], V[0] = r, p
+        V[1] = (1.0 / c) * AP + (-d / c) * V[0]
+        for j in range(1, k + 1):
+            if j == 1:
+                U[1] = (1.0 / c) * A.dot(U[0]) + (-d / c) * U[0]
+            else:
+                U[j] = ((2.0 / c) * A.dot(U[j - 1]) + (-2.0 * d / c) * U[j - 1]) + (-1.0) * U[j - 2]
+            V[j + 1] = ((2.0 / c) * A.dot(V[j]) + (-2.0 * d / c) * V[j]) + (-1.0) * V[j - 1]
+        coef = coef_fn(gram_layout_cg(U, V, k), k, c, d)
+        for j in range(k + 1):
+            al, be = coef[2 * j], coef[2 * j + 1]
+            x = x + al * p
+            r = r - al * AP
+            p = r + be * p
+            AP = A.dot(p)
+        it += k + 1
+        nosl.append(it)
+    else:
+        res.append(norm(r) / bn)
+    return x, {"residual": np.array(res), "nosl": np.array(nosl[:len(res)]), "converged": converged}

@@ -8,6 +8,7 @@
 extern "C" {
 void host_kskipcg_coef(const double* G, int k, double* coef) { pk_kskipcg_coef(G, k, coef); }
 void host_kskipmrr_coef(const double* G, int k, double* coef) { pk_kskipmrr_coef(G, k, coef); }
+void host_kskipcg_coef_cheb(const double* G, int k, double c, double d, double* coef) { pk_kskipcg_coef_cheb(G, k, c, d, coef); }
 void host_kskipmrr_coef_cheb(const double* G, int k, double c, double d, double* coef) { pk_kskipmrr_coef_cheb(G, k, c, d, coef); }
 
 void* hs_new(long long maxiter, double tol, int k, long long hist_len, double* res, long long* nosl, long long* khist) {

@@ -24,14 +24,16 @@ def host_lib(tmp_path_factory):
     lib = C.CDLL(str(out))
     lib.host_kskipmrr_coef_cheb.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
     lib.host_kskipmrr_coef_cheb.restype = None
+    lib.host_kskipcg_coef_cheb.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    lib.host_kskipcg_coef_cheb.restype = None
     return lib
 
 
-def _device_coefficients(lib):
+def _device_coefficients(lib, cg=False):
     def fn(G, k, c, d):
         G = np.ascontiguousarray(G)
         coef = np.zeros(2 * (k + 1))
-        lib.host_kskipmrr_coef_cheb(G.ctypes.data, k, c, d, coef.ctypes.data)
+        (lib.host_kskipcg_coef_cheb if cg else lib.host_kskipmrr_coef_cheb)(G.ctypes.data, k, c, d, coef.ctypes.data)
         return coef
     return fn
 
@@ -92,3 +94,23 @@ def test_monomial_basis_has_lost_the_history_where_chebyshev_has_not():
     xc, ic = cheb.kskipmrr_chebyshev(A, b, tol=1e-8, k=12)
     assert int(ik["nosl"][-1]) > 5 * int(im["nosl"][-1])        # monomial: an order of magnitude more iterations
     assert int(ic["nosl"][-1]) <= int(im["nosl"][-1]) + 13
+
+
+@pytest.mark.parametrize("name", sorted(SYSTEMS))
+@pytest.mark.parametrize("k", [4, 8, 12])
+def test_chebyshev_kskipcg_follows_plain_cg(host_lib, name, k):
+    """Same for k-skip CG: through the device's engine (host build) the Chebyshev-basis trips follow plain CG where the
+    reference's monomial k = 12 trip needs 5000 iterations instead of 65."""
+    kind, args = SYSTEMS[name]
+    A = problems.to_scipy(*getattr(problems, kind)(*args))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    xc, ic = oracle.cg(A, b.copy(), tol=1e-8)
+    x, info = cheb.kskipcg_chebyshev(A, b, tol=1e-8, k=k, coef_fn=_device_coefficients(host_lib, cg=True))
+    x2, info2 = cheb.kskipcg_chebyshev(A, b, tol=1e-8, k=k)
+    assert np.array_equal(info["residual"], info2["residual"]) and np.array_equal(x, x2)      # engine == numpy, bit for bit
+    assert info["converged"]
+    it, it_cg = int(info["nosl"][-1]), int(ic["nosl"][-1])
+    assert it_cg <= it <= it_cg + k + 1
+    sel = info["nosl"][info["nosl"] <= min(50, it_cg)]
+    np.testing.assert_allclose(info["residual"][:len(sel)], ic["residual"][sel], rtol=1e-8)
+    assert oracle.true_relres(A, b, x) < 1e-8 * (1 + 1e-6)

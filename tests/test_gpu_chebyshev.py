@@ -48,4 +48,25 @@ def test_chebyshev_matches_its_numpy_restatement_and_explicit_bounds():
     x2, info2 = pk.kskipmrr(A, b, tol=1e-8, k=8, basis=("chebyshev", lo, hi), use_graph=False)
     assert torch.equal(info2["residual"], info["residual"]) and torch.equal(x2, x)
     with pytest.raises(pk.PkError):
-        pk.kskipcg(A, b, k=2, basis="chebyshev")
+        pk.mrr(A, b, basis="chebyshev")
+
+
+_CGG = [c for c in CASES if c["solver"] == "cg" and c["maxiter"] is None and c["tol"] == 1e-8
+        and c["rhs"] == "randn" and c["matrix"] in ("p2d48", "p3d16", "p3d32", "p3d12x20x9")]
+
+
+@pytest.mark.parametrize("k", [4, 8, 12])
+@pytest.mark.parametrize("case", _CGG, ids=[c["id"] for c in _CGG])
+def test_chebyshev_kskipcg_matches_the_reference_cg_history(case, k):
+    import parallel_krylov_b200 as pk
+    gold = load(case)                                   # plain CG of the unmodified reference
+    mat, b = inputs(case)
+    x, info = pk.kskipcg(mat, b, tol=1e-8, k=k, basis="chebyshev")
+    nosl = info["nosl"].cpu().numpy()
+    res = info["residual"].cpu().numpy()
+    it_cg = int(gold["nosl"][-1])
+    assert info["converged"]
+    assert it_cg <= int(nosl[-1]) <= it_cg + k + 1
+    sel = nosl[nosl <= min(50, it_cg)]
+    np.testing.assert_allclose(res[:len(sel)], gold["residual"][sel], rtol=1e-8)
+    assert oracle.true_relres(mat, b, x.cpu().numpy()) < 1e-8 * (1 + 1e-6)
