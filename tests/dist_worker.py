@@ -19,6 +19,20 @@ from parallel_krylov_b200 import problems
 from parallel_krylov_b200 import mpi as pkm
 
 
+def _random_spd(n, seed):
+    """Sparse symmetric, strictly diagonally dominant (=> SPD), columns spread over the whole index range."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    B = sp.random(n, n, density=6.0 / n, random_state=rng, format="csr", data_rvs=lambda m: -rng.uniform(0.1, 1.0, m))
+    S = (B + B.T).tocsr()
+    S.setdiag(0.0)
+    S.eliminate_zeros()
+    d = np.asarray(abs(S).sum(axis=1)).ravel() + 1.0
+    A = (S + sp.diags(d)).tocsr()
+    A.sort_indices()
+    return A
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -29,6 +43,8 @@ def main():
         "p3d_9x7x11": problems.to_scipy(*problems.poisson3d(9, 7, 11)),       # rows not divisible by the ranks
         "band27": problems.to_scipy(*problems.banded_spd(30011, 13, 0)),
         "dense": problems.dense_spd(384, 0),
+        # unstructured: every rank exchanges with every other rank, send lists are not contiguous runs
+        "random": _random_spd(6007, 0),
     }
     cases = [("cg", None), ("mrr", None), ("kskipcg", 2), ("kskipmrr", 2), ("kskipmrr", 4), ("adaptivekskipmrr", 4),
              ("cgcg", None)]
