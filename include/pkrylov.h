@@ -140,9 +140,14 @@ int pk_spmv(pk_ctx* ctx, pk_mat* mat, double* d_x, double* d_y, double* d_x1, do
 /* Matrix-powers kernel: levels l = 1..k of BOTH k-skip basis chains, (A^l u, A^l v), in ONE pass over A, written to
  * d_base0 + l*ld and d_base1 + l*ld (ld = pk_mat_ld) from level 0 at d_base0 / d_base1 — bit-identical to k sequential
  * pk_spmv calls.  Replaces the basis loops v3/cpu/kskipmrr.py:45-48, v3/cpu/kskipcg.py:36-39 for operators of small
- * bandwidth (square single-GPU CSR block, rows of <= 28 nonzeros, half bandwidth bw with 640 - 2(k-1)bw >= 320);
+ * bandwidth (square CSR block, rows of <= 28 nonzeros, half bandwidth bw with W - 2(k-1)bw >= W/2 for the window W of
+ * the kernel that applies: 640 rows in general, 1024 when every row holds its full band of <= 27 diagonals);
  * PK_ERR_UNSUPPORTED otherwise (the solvers then use k two-chain SpMV passes). */
 int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1);
+/* Which matrix-powers kernel pk_matpow / the k-skip solvers would run for this operator and k: *kind = 0 none (two-chain
+ * SpMV passes), 1 general small-bandwidth kernel (one row per thread), 2 dense-band kernel (two rows per thread);
+ * *window_rows = rows per block before the trapezoid overlap is taken off (blocking on first use: probes the structure). */
+int pk_mat_matpow_info(pk_ctx* ctx, pk_mat* mat, int k, int* kind, int* window_rows);
 /* Row-partitioned matrix powers: register copies of the neighbours' rows of A next to this block — the last `rows_above`
  * rows of the previous rank and the first `rows_below` rows of the next one, as CSR with GLOBAL int32 column indices
  * (device arrays, borrowed) — so that the basis of a trip needs ONE exchange of depth rows + half_bw instead of one per

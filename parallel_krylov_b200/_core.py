@@ -170,6 +170,12 @@ class Operator:
         return {"kernel": "row-pattern" if self.compressed else ["csr-stream", "csr-vector", "dense-gemv"][k.value],
                 "tile_rows": r.value, "tile_cap": c.value, "patterns": self.n_patterns}
 
+    def matpow_info(self, k: int):
+        """Which one-pass basis kernel a k-skip solve with this k would use (csrc/pk_matpow.cu)."""
+        kind, win = C.c_int(), C.c_int()
+        check(self.ctx.lib.pk_mat_matpow_info(self.ctx.handle, self.handle, int(k), C.byref(kind), C.byref(win)))
+        return {"kernel": ["none", "general", "dense-band"][kind.value], "window_rows": win.value}
+
     # -- constructors -------------------------------------------------------------------------------------------
     @classmethod
     def from_csr_tensors(cls, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n_cols: int,

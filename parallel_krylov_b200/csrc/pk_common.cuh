@@ -160,6 +160,7 @@ struct pk_mat {
     int mp_bw = 0;           // half bandwidth max |col - row|
     // row-partitioned matrix powers (pk_mat_set_matpow_ext): ghost rows of A from the two neighbours, level-0 ghost inputs
     bool mp_ext = false;
+    bool mp_dense = false;   // every row holds its full band: the two-rows-per-thread kernel applies
     long long mp_row0 = 0, mp_n_global = 0;
     const long long* mp_halo_global = nullptr;                 // borrowed
     const int32_t* mp_g_rowptr[2] = {nullptr, nullptr};        // borrowed: ghost rows above / below (global columns)

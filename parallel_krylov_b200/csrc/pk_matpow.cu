@@ -163,6 +163,189 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
     }
 }
 
+// ---- dense band: two rows per thread, the next window's values staged by TMA ----------------------------------------
+// When EVERY row holds its full band (row r has exactly the columns max(r-bw,0) .. min(r+bw,n-1): the banded system of
+// BASELINE.json configs[3]), a thread that owns the two adjacent rows 2t, 2t+1 needs the 2bw+2 consecutive entries
+// x[2t-bw .. 2t+1+bw] of a level, and every one of them but the two outermost feeds BOTH rows: 2bw+2 shared loads for
+// two rows instead of 2(2bw+1).  No column offsets are kept or decoded (entry e of a row is diagonal e + max(bw-r,0)),
+// and the window grows to 2*NT rows, which also trims the trapezoid overlap (1.40x -> 1.26x at k = 8, bw = 13).  A level
+// lives in shared memory split by parity of the window position (even positions in E, odd in O), so that consecutive
+// threads read consecutive 16-byte words whichever position they ask for.
+// The values of a window are one contiguous run of the CSR value array (no column indices are read at all).  Row-per-thread
+// loads of that run touch 32 different sectors per warp instruction and kept the first version of this kernel L1-bound
+// (measured: 7.9 ms against 9.1 ms of k_matpow), so the run of the NEXT window is fetched by TMA bulk copies into shared
+// memory WHILE the levels of the current one are computed; at the top of a window the threads move their two rows from
+// shared memory to registers.  DRAM time hides behind the level computation.
+// Entries clipped at the matrix edge are kept as +0.0 values: they meet positions outside the matrix, which hold +0.0 at
+// every level, and a running sum that starts at +0.0 is unchanged by adding (+-0.0) — results stay bit-identical to k
+// chained mat-vecs (tests/test_gpu_kernels.py).
+constexpr int MB_DMAX = 27;     // diagonals per row kept in registers (bw <= 13)
+constexpr int MB_PAD = 14;      // a level holds 2 NT + 2 bw <= 2 (NT + MB_PAD) positions
+
+template <int NT>
+struct MbLayout {
+    static constexpr int T2 = 2 * NT;                          // rows per window
+    static constexpr int H = NT + MB_PAD;                      // 16-byte words of E (and of O) per level
+    static constexpr size_t off_levels = 16;                   // after the mbarrier
+    static constexpr size_t off_a = off_levels + sizeof(double2) * 4 * H;
+    static constexpr size_t a_doubles = (size_t)T2 * MB_DMAX + 2 + 32;   // + slack: a predicated-off read may be speculated
+    static constexpr size_t bytes = off_a + sizeof(double) * a_doubles;
+};
+
+// values of window rows [f, e) -> shared memory by bulk copies (one thread); returns nothing, completion on `bar`.
+// The run starts at the even element q_al <= rowptr[f] (16-byte aligned source); an odd last element is moved by hand.
+__device__ __forceinline__ void mb_issue_window(const MpArgs& a, long long s0, int T2, double* smA, unsigned long long* bar) {
+    long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
+    const long long q0 = __ldg(a.rowptr + f), q1 = __ldg(a.rowptr + e);
+    const long long q_al = q0 & ~1ll;
+    const long long cnt = q1 - q_al;
+    const unsigned bytes = (unsigned)((cnt & ~1ll) * 8);
+    if (cnt & 1) smA[cnt - 1] = __ldg(a.val + q1 - 1);
+    mbar_expect_tx(bar, bytes);                                // also the single arrival of this phase (bytes may be 0)
+    constexpr unsigned PIECE = 16384;
+    for (unsigned o = 0; o < bytes; o += PIECE)
+        bulk_g2s((char*)smA + o, (const char*)(a.val + q_al) + o, (bytes - o < PIECE) ? bytes - o : PIECE, bar);
+    // level 0 of that window and its row pointers -> L2, so that the top of the next window does not wait for DRAM
+    const long long g0 = (s0 - MB_PAD < 0 ? 0 : s0 - MB_PAD) & ~1ll;
+    long long g1 = s0 + T2 + MB_PAD > a.n ? a.n : s0 + T2 + MB_PAD;
+    g1 &= ~1ll;
+    if (g1 > g0 && (((unsigned long long)a.base0 | (unsigned long long)a.base1) & 15ull) == 0) {
+        const unsigned vb = (unsigned)((g1 - g0) * 8);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.base0 + g0), "r"(vb) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.base1 + g0), "r"(vb) : "memory");
+    }
+}
+
+// BWT > 0: half bandwidth known at compile time (13: the 27-diagonal band of configs[3]) — the level loop is then
+// straight-line code (28 shared loads with immediate offsets, 108 multiplies, 108 adds) and the loads are scheduled ahead
+// of the arithmetic; BWT = 0 keeps bw a run-time value (uniform branches per position).
+template <int NT, int BWT>
+__global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    const int k = a.dyn ? ra.st->k : a.k;
+    if (k < 1) return;
+    using L = MbLayout<NT>;
+    constexpr int T2 = L::T2, H = L::H;
+    const int bw = BWT ? BWT : a.bw;
+    const int D = 2 * bw + 1;
+    const int ghost = (k - 1) * bw;
+    const int t_out = T2 - 2 * ghost;
+    extern __shared__ __align__(16) unsigned char mb_raw[];
+    unsigned long long* bar = (unsigned long long*)mb_raw;
+    double2* lev = (double2*)(mb_raw + L::off_levels);          // [buffer 0..1][E | O][H], both chains interleaved per position
+    double* smA = (double*)(mb_raw + L::off_a);                 // the values of one window, as they lie in the CSR array
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * H; i += NT) lev[i] = make_double2(0.0, 0.0);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n_tiles = (a.n + t_out - 1) / t_out;
+    if (tid == 0 && blockIdx.x < n_tiles) mb_issue_window(a, (long long)blockIdx.x * t_out - ghost, T2, smA, bar);
+    unsigned phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long o0 = tile * t_out;
+        const long long o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
+        const long long s0 = o0 - ghost;                // first row of the window (position 0)
+        const long long rA = s0 + 2 * tid, rB = rA + 1;
+        // ---- where my two rows sit in the staged run
+        const long long f = s0 < 0 ? 0 : s0;
+        const long long q_al = (long long)__ldg(a.rowptr + f) & ~1ll;
+        int qA = 0, cA = 0, qB = 0, cB = 0;
+        if (rA >= 0 && rA < a.n) {
+            const int q = __ldg(a.rowptr + rA), q2 = __ldg(a.rowptr + rA + 1);
+            qA = (int)(q - q_al); cA = q2 - q;
+            qB = (int)(q2 - q_al);                      // row B follows row A in the run
+        }
+        if (rB >= 0 && rB < a.n) {
+            if (rB == 0) qB = (int)(__ldg(a.rowptr + rB) - q_al);
+            cB = __ldg(a.rowptr + rB + 1) - (int)(qB + q_al);
+        }
+        // ---- level 0 of both chains; position p (row s0 + p) sits at index p + bw, even indices in E, odd in O: the
+        // entries a thread gathers are then at the compile-time indices 2 tid + s, s = 0 .. 2 bw + 1
+        double2* P = lev;
+        double2* N = lev + 2 * H;
+        for (int i = tid; i < T2 + 2 * bw; i += NT) {
+            const long long g = s0 - bw + i;
+            double u0 = 0.0, u1 = 0.0;
+            if (g >= 0 && g < a.n) { u0 = a.base0[g]; u1 = a.base1[g]; }
+            P[(i & 1) * H + (i >> 1)] = make_double2(u0, u1);
+        }
+        // ---- my two rows: shared memory -> registers (diagonal d of row r is its entry d - max(bw - r, 0))
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        double vA[MB_DMAX], vB[MB_DMAX];
+        if (s0 >= bw && s0 + T2 + bw <= a.n) {          // window clear of the matrix edges: every row is full
+            const double* sA = smA + qA;
+#pragma unroll
+            for (int d = 0; d < MB_DMAX; ++d) {
+                if (d < D) { vA[d] = sA[d]; vB[d] = sA[D + d]; }
+                else { vA[d] = 0.0; vB[d] = 0.0; }
+            }
+        } else {
+            const int dA = rA < bw ? (int)(bw - rA) : 0, dB = rB < bw ? (int)(bw - rB) : 0;
+#pragma unroll
+            for (int d = 0; d < MB_DMAX; ++d) {
+                const int eA = d - dA, eB = d - dB;
+                vA[d] = (eA >= 0 && eA < cA) ? smA[qA + eA] : 0.0;
+                vB[d] = (eB >= 0 && eB < cB) ? smA[qB + eB] : 0.0;
+            }
+        }
+        __syncthreads();                                // level 0 visible; everyone is done with the staged values
+        if (tid == 0 && tile + gridDim.x < n_tiles)     // the next window of this block streams in behind the levels
+            mb_issue_window(a, (tile + gridDim.x) * t_out - ghost, T2, smA, bar);
+        // my rows' own positions: index 2 tid + bw (row A) and 2 tid + bw + 1 (row B)
+        const int wA = ((bw & 1) ? H : 0) + tid + (bw >> 1);
+        const int wB = (((bw + 1) & 1) ? H : 0) + tid + ((bw + 1) >> 1);
+        for (int l = 1; l <= k; ++l) {
+            double yA0 = 0.0, yA1 = 0.0, yB0 = 0.0, yB1 = 0.0;
+            const double2* Pt = P + tid;
+#pragma unroll
+            for (int s = 0; s <= MB_DMAX; ++s) {
+                if (s > D) break;                        // uniform: positions 2 tid - bw + s, s = 0 .. 2 bw + 1
+                const double2 X = Pt[(s & 1) * H + (s >> 1)];
+                if (s < MB_DMAX) {
+                    if (s < D) {                         // row A, diagonal s
+                        yA0 += vA[s] * X.x;
+                        yA1 += vA[s] * X.y;
+                    }
+                }
+                if (s >= 1) {                            // row B, diagonal s - 1 (same position, one row further down)
+                    yB0 += vB[s - 1] * X.x;
+                    yB1 += vB[s - 1] * X.y;
+                }
+            }
+            N[wA] = make_double2(yA0, yA1);
+            N[wB] = make_double2(yB0, yB1);
+            if (rA >= o0 && rA < o1) {
+                a.base0[(size_t)l * a.ld + rA] = yA0;
+                a.base1[(size_t)l * a.ld + rA] = yA1;
+            }
+            if (rB >= o0 && rB < o1) {
+                a.base0[(size_t)l * a.ld + rB] = yB0;
+                a.base1[(size_t)l * a.ld + rB] = yB1;
+            }
+            __syncthreads();
+            double2* t0 = P; P = N; N = t0;
+        }
+    }
+}
+
+// Is the block a dense band of half width bw?  out[0] counts the rows that are not.
+__global__ void k_band_dense(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, long long n, int bw, int* out) {
+    int bad = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const long long lo = r - bw < 0 ? 0 : r - bw, hi = r + bw > n - 1 ? n - 1 : r + bw;
+        const int q0 = rowptr[r], q1 = rowptr[r + 1];
+        if (q1 - q0 != (int)(hi - lo + 1)) bad = 1;
+        else
+            for (int q = q0; q < q1; ++q)
+                if (col[q] != (int)(lo + (q - q0))) { bad = 1; break; }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(out, 1);
+}
+
 __global__ void k_band_info(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, long long n_rows,
                             long long row0, int* out) {
     int mlen = 0, mbw = 0;
@@ -226,8 +409,43 @@ static int band_info(pk_ctx* ctx, pk_mat* m) {
     PK_CHECK(band_probe(ctx, m->rowptr, m->col, m->n_rows, 0, h));
     m->mp_rmax = h[0];
     m->mp_bw = h[1];
+    if (m->mp_bw >= 1 && 2 * m->mp_bw + 1 <= MB_DMAX && m->mp_rmax <= MB_DMAX && m->n_rows > 2 * m->mp_bw &&
+        ((uintptr_t)m->val & 15) == 0) {           // the TMA bulk copies of the value runs need a 16-byte aligned array
+        int* d = nullptr;
+        int bad = 1;
+        PK_CUDA(cudaMalloc(&d, sizeof(int)));
+        PK_CUDA(cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+        int grid = (int)((m->n_rows + 255) / 256);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        k_band_dense<<<grid, 256, 0, ctx->stream>>>(m->rowptr, m->col, m->n_rows, m->mp_bw, d);
+        PK_CUDA(cudaGetLastError());
+        PK_CUDA(cudaMemcpyAsync(&bad, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d);
+        m->mp_dense = (bad == 0);
+    }
     return PK_OK;
 }
+
+// Window of the kernel that will run: rows per block, before the trapezoid is taken off.
+static int band_threads() {
+    static int nt = -1;
+    if (nt < 0) {
+        const char* e = getenv("PK_MATPOW_NT");
+        nt = e ? atoi(e) : 448;
+        if (nt != 384 && nt != 448) nt = 448;
+    }
+    return nt;
+}
+static bool band_kernel_on(const pk_mat* m) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PK_MATPOW_BAND");
+        enabled = e ? atoi(e) : 1;
+    }
+    return enabled && m->mp_dense && !m->distributed;
+}
+static int mp_window(const pk_mat* m) { return band_kernel_on(m) ? 2 * band_threads() : MP_T; }
 
 extern "C" int pk_mat_set_matpow_ext(pk_mat* m, int half_bw, int max_row_nnz, int64_t row0, int64_t n_global,
                                      const int64_t* d_halo_global, int64_t rows_above, const int32_t* d_rowptr_above,
@@ -277,7 +495,8 @@ bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k) {
         if ((ctx->rank > 0 && m->mp_g_rows[0] < need) || (ctx->rank + 1 < ctx->n_ranks && m->mp_g_rows[1] < need)) return false;
     } else if (band_info(ctx, m) != PK_OK) return false;
     if (m->mp_rmax > MP_RMAX || m->mp_bw > 127 || m->mp_bw < 1) return false;
-    return MP_T - 2 * (k - 1) * m->mp_bw >= MP_T / 2;
+    const int win = mp_window(m);
+    return win - 2 * (k - 1) * m->mp_bw >= win / 2;
 }
 
 int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn) {
@@ -313,6 +532,30 @@ int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1
     ra.only_rollback = ctx->ctl_only_rollback;
     ra.dyn_cj = -1;
     ra.dyn_last = 0;
+    if (band_kernel_on(m)) {
+        const int nt = band_threads();
+        const size_t smem = nt == 384 ? MbLayout<384>::bytes : MbLayout<448>::bytes;
+        const bool b13 = a.bw == 13;
+        const void* kb = nt == 384 ? (b13 ? (const void*)k_matpow_band<384, 13> : (const void*)k_matpow_band<384, 0>)
+                                   : (b13 ? (const void*)k_matpow_band<448, 13> : (const void*)k_matpow_band<448, 0>);
+        pk_blocks_per_sm(kb, nt, smem);              // opts in to the dynamic shared memory size
+        const int t_out = 2 * nt - 2 * (k - 1) * a.bw;
+        const long long n_tiles = (a.n + t_out - 1) / t_out;
+        int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+        if (grid < 1) grid = 1;
+        if (nt == 384 && b13) k_matpow_band<384, 13><<<grid, 384, smem, ctx->stream>>>(a, ra);
+        else if (nt == 384) k_matpow_band<384, 0><<<grid, 384, smem, ctx->stream>>>(a, ra);
+        else if (b13) k_matpow_band<448, 13><<<grid, 448, smem, ctx->stream>>>(a, ra);
+        else k_matpow_band<448, 0><<<grid, 448, smem, ctx->stream>>>(a, ra);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            pk_set_error("matrix-powers (dense band) launch: %s", cudaGetErrorString(e));
+            return PK_ERR_CUDA;
+        }
+        ctx->launches++;
+        ctx->spmvs += 2LL * k;
+        return PK_OK;
+    }
     const size_t smem = sizeof(double) * 4 * (size_t)(MP_T + 2 * a.bw);
     const void* kern = ext ? (const void*)k_matpow<true> : (const void*)k_matpow<false>;
     pk_blocks_per_sm(kern, MP_T, smem);          // opts in to the dynamic shared memory size if needed
@@ -332,6 +575,15 @@ int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1
     return PK_OK;
 }
 
+extern "C" int pk_mat_matpow_info(pk_ctx* ctx, pk_mat* mat, int k, int* kind, int* window_rows) {
+    PK_REQUIRE(ctx && mat && kind && window_rows, "null argument");
+    PK_CUDA(cudaSetDevice(ctx->device));
+    const bool ok = pk_matpow_ok(ctx, mat, k);
+    *kind = !ok ? 0 : (band_kernel_on(mat) ? 2 : 1);
+    *window_rows = ok ? mp_window(mat) : 0;
+    return PK_OK;
+}
+
 // C-ABI building block (tests / benchmarks): levels 1..k of both chains from level 0 at d_base0 / d_base1.
 extern "C" int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1) {
     PK_REQUIRE(ctx && mat && d_base0 && d_base1, "null argument");
@@ -339,7 +591,8 @@ extern "C" int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, doubl
     PK_CUDA(cudaSetDevice(ctx->device));
     if (!pk_matpow_ok(ctx, mat, k < 2 ? 2 : k)) {
         pk_set_error("operator not eligible for the one-pass matrix-powers kernel (needs a square single-GPU CSR block, "
-                     "rows of <= %d nonzeros, half bandwidth bw with 640 - 2(k-1)bw >= 320; PK_MATPOW=0 disables it)", MP_RMAX);
+                     "rows of <= %d nonzeros, half bandwidth bw with W - 2(k-1)bw >= W/2 for the window W = 640 rows, or 1024 "
+                     "for a dense band; PK_MATPOW=0 disables it)", MP_RMAX);
         return PK_ERR_UNSUPPORTED;
     }
     PK_CUDA(cudaMemsetAsync(&ctx->d_state->done, 0, sizeof(int), ctx->stream));

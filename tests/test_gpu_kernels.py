@@ -212,15 +212,34 @@ def test_solvers_on_compressed_operator_match_csr_bitwise(pk, solver, k):
         assert torch.equal(x0, x1)
 
 
-@pytest.mark.parametrize("n,half_bw,k", [(30011, 13, 8), (5000, 2, 4), (700, 13, 2), (100003, 13, 5)])
-def test_matrix_powers_one_pass_is_bitwise_k_sequential_spmvs(pk, n, half_bw, k):
+def _band_with_holes(n, half_bw, seed):
+    """The dense band with a third of its off-diagonal entries removed (symmetrically): same bandwidth, ragged rows."""
+    import scipy.sparse as sp
+    A = problems.to_scipy(*problems.banded_spd(n, half_bw, seed)).tocoo()
+    lo, hi = np.minimum(A.row, A.col).astype(np.int64), np.maximum(A.row, A.col).astype(np.int64)
+    keep = (A.row == A.col) | ((lo * 2654435761 + hi * 40503) % 3 != 0)
+    B = sp.csr_matrix((A.data[keep], (A.row[keep], A.col[keep])), shape=A.shape)
+    B.sort_indices()
+    return B
+
+
+@pytest.mark.parametrize("n,half_bw,k,structure", [
+    (30011, 13, 8, "dense"), (5000, 2, 4, "dense"), (700, 13, 2, "dense"), (100003, 13, 5, "dense"),
+    (27, 13, 2, "dense"), (1024, 13, 8, "dense"), (843, 13, 8, "dense"), (4099, 1, 8, "dense"), (60013, 13, 16, "dense"),
+    (200003, 6, 12, "dense"),
+    (30011, 13, 8, "holes"), (5000, 2, 4, "holes"), (700, 13, 2, "holes"), (100003, 13, 5, "holes")])
+def test_matrix_powers_one_pass_is_bitwise_k_sequential_spmvs(pk, n, half_bw, k, structure):
     """k levels of both basis chains in ONE pass over A (csrc/pk_matpow.cu) == k sequential operator applications,
-    bit for bit (same per-row left-to-right sums) — including windows cut by the matrix ends."""
+    bit for bit (same per-row left-to-right sums) — including windows cut by the matrix ends.  A full band runs the
+    two-rows-per-thread kernel, a band with holes the general one."""
     import ctypes as C
     from parallel_krylov_b200 import _lib
     from parallel_krylov_b200._core import _ptr
-    A = problems.to_scipy(*problems.banded_spd(n, half_bw, 1))
+    A = problems.to_scipy(*problems.banded_spd(n, half_bw, 1)) if structure == "dense" else _band_with_holes(n, half_bw, 1)
     op = pk.Operator.from_any(A)
+    info = op.matpow_info(k)
+    if os.environ.get("PK_MATPOW_BAND", "1") not in ("0", ""):
+        assert info["kernel"] == ("dense-band" if structure == "dense" else "general"), info
     ctx, ld = op.ctx, op.ld
     rng = np.random.default_rng(k)
     u0, v0 = rng.standard_normal(n), rng.standard_normal(n)
