@@ -93,19 +93,19 @@ def algorithmic_bytes(solver, k, n, nnz):
 def one_pass_basis(name):
     """Does the workload's operator qualify for the one-pass matrix-powers kernel (csrc/pk_matpow.cu: half bandwidth bw
     with W - 2(k-1)bw >= W/2; the banded workloads are full bands of <= 27 diagonals, whose kernel has a window of W =
-    1024 rows)?  Only the banded systems do; 3-D stencils have bw = nx*ny."""
+    768 rows)?  Only the banded systems do; 3-D stencils have bw = nx*ny."""
     solver, k, kind, dims, _ = WORKLOADS[name]
     if kind != "banded" or not k or k < 2 or os.environ.get("PK_MATPOW", "1") in ("0", ""):
         return False
-    return 1024 - 2 * (k - 1) * dims[1] >= 512 and 2 * dims[1] + 1 <= 27
+    return 768 - 2 * (k - 1) * dims[1] >= 384 and 2 * dims[1] + 1 <= 27
 
 
 def actual_bytes(solver, k, n, nnz, matpow=False):
     """Bytes the code REALLY moves per solver iteration with the default kernels (every array pass counted once, x
     gathers counted as one pass): the k-skip basis reads A once for both chains and the step SpMVs consume A·v in
     registers, so a trip makes 2k+1 passes over A, not the 3k+2 of §8d's formula — and k+2 passes when the one-pass
-    matrix-powers kernel generates the basis (matpow: the dense-band kernel reads the values and row pointers only, no
-    column indices; ghost-row re-reads of A are served by L2 and not counted)."""
+    matrix-powers kernel generates the basis (matpow: the dense-band kernel reads the values only — no column indices,
+    no row pointers; ghost-row re-reads of A are served by L2 and not counted)."""
     b_a = 12.0 * nnz + 4.0 * (n + 1)                     # one pass over the CSR arrays
     if solver == "cg":                                   # SpMV (A, p, v) + xr (4R 2W) + p (2R 1W)
         return b_a + 16.0 * n + 72.0 * n
@@ -116,7 +116,7 @@ def actual_bytes(solver, k, n, nnz, matpow=False):
     first = 56.0 if solver == "kskipcg" else 72.0        # un-fused first step of a trip
     fused = 48.0 if solver == "kskipcg" else 64.0        # step fused into the SpMV epilogue: vectors read + written
     if matpow:
-        a_once = b_a if matpow == "general" else 8.0 * nnz + 4.0 * (n + 1)
+        a_once = b_a if matpow == "general" else 8.0 * nnz
         basis = a_once + (2 + 2 * k) * 8.0 * n           # one pass over A, 2 inputs read, 2k level vectors written
     else:
         basis = k * (b_a + 32.0 * n)                     # k two-chain passes: A + 2 gathers + 2 stores each

@@ -141,7 +141,7 @@ int pk_spmv(pk_ctx* ctx, pk_mat* mat, double* d_x, double* d_y, double* d_x1, do
  * d_base0 + l*ld and d_base1 + l*ld (ld = pk_mat_ld) from level 0 at d_base0 / d_base1 — bit-identical to k sequential
  * pk_spmv calls.  Replaces the basis loops v3/cpu/kskipmrr.py:45-48, v3/cpu/kskipcg.py:36-39 for operators of small
  * bandwidth (square CSR block, rows of <= 28 nonzeros, half bandwidth bw with W - 2(k-1)bw >= W/2 for the window W of
- * the kernel that applies: 640 rows in general, 1024 when every row holds its full band of <= 27 diagonals);
+ * the kernel that applies: 640 rows in general, 768 when every row holds its full band of <= 27 diagonals);
  * PK_ERR_UNSUPPORTED otherwise (the solvers then use k two-chain SpMV passes). */
 int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, double* d_base1);
 /* Which matrix-powers kernel pk_matpow / the k-skip solvers would run for this operator and k: *kind = 0 none (two-chain

@@ -163,69 +163,88 @@ __global__ void __launch_bounds__(MP_T, 1) k_matpow(MpArgs a, PkRedArgs ra) {
     }
 }
 
-// ---- dense band: two rows per thread, the next window's values staged by TMA ----------------------------------------
+// ---- dense band: two rows per thread, the next window staged by TMA --------------------------------------------------
 // When EVERY row holds its full band (row r has exactly the columns max(r-bw,0) .. min(r+bw,n-1): the banded system of
 // BASELINE.json configs[3]), a thread that owns the two adjacent rows 2t, 2t+1 needs the 2bw+2 consecutive entries
 // x[2t-bw .. 2t+1+bw] of a level, and every one of them but the two outermost feeds BOTH rows: 2bw+2 shared loads for
 // two rows instead of 2(2bw+1).  No column offsets are kept or decoded (entry e of a row is diagonal e + max(bw-r,0)),
-// and the window grows to 2*NT rows, which also trims the trapezoid overlap (1.40x -> 1.26x at k = 8, bw = 13).  A level
-// lives in shared memory split by parity of the window position (even positions in E, odd in O), so that consecutive
-// threads read consecutive 16-byte words whichever position they ask for.
-// The values of a window are one contiguous run of the CSR value array (no column indices are read at all).  Row-per-thread
-// loads of that run touch 32 different sectors per warp instruction and kept the first version of this kernel L1-bound
-// (measured: 7.9 ms against 9.1 ms of k_matpow), so the run of the NEXT window is fetched by TMA bulk copies into shared
-// memory WHILE the levels of the current one are computed; at the top of a window the threads move their two rows from
-// shared memory to registers.  DRAM time hides behind the level computation.
+// the row pointers follow from (n, bw) in closed form, and the window grows to 2*NT rows, which also trims the trapezoid
+// overlap (1.40x -> 1.31x at k = 8, bw = 13).  A level lives in shared memory split by parity of the window position (even
+// positions in E, odd in O), so that consecutive threads read consecutive 16-byte words whichever position they ask for.
+// The values of a window are ONE contiguous run of the CSR value array.  Row-per-thread global loads of that run touch 32
+// different sectors per warp instruction and kept the first version of this kernel L1-bound (measured: 7.9 ms against
+// 9.1 ms of k_matpow), so the run of the NEXT window — and level 0 of both chains for it — is fetched by TMA bulk copies
+// into shared memory WHILE the levels of the current one are computed; at the top of a window the threads move their two
+// rows from shared memory to registers (27 conflict-free 128-bit loads).  DRAM time hides behind the arithmetic: the
+// kernel ends up bound by the FP64 pipe (4 multiply-adds per nonzero per level, issued as DMUL + DADD for bit parity).
 // Entries clipped at the matrix edge are kept as +0.0 values: they meet positions outside the matrix, which hold +0.0 at
 // every level, and a running sum that starts at +0.0 is unchanged by adding (+-0.0) — results stay bit-identical to k
 // chained mat-vecs (tests/test_gpu_kernels.py).
 constexpr int MB_DMAX = 27;     // diagonals per row kept in registers (bw <= 13)
-constexpr int MB_PAD = 14;      // a level holds 2 NT + 2 bw <= 2 (NT + MB_PAD) positions
+constexpr int MB_BWMAX = 13;
+constexpr int MB_NT = 384;      // threads per block: 768-row windows, <= 168 registers per thread
 
-template <int NT>
 struct MbLayout {
-    static constexpr int T2 = 2 * NT;                          // rows per window
-    static constexpr int H = NT + MB_PAD;                      // 16-byte words of E (and of O) per level
+    static constexpr int T2 = 2 * MB_NT;                       // rows per window
+    static constexpr int H = MB_NT + MB_BWMAX + 1;             // 16-byte words of E (and of O) per level
+    static constexpr int SW = T2 + 2 * MB_BWMAX + 2;           // doubles per chain of the staged level 0 (even)
     static constexpr size_t off_levels = 16;                   // after the mbarrier
-    static constexpr size_t off_a = off_levels + sizeof(double2) * 4 * H;
+    static constexpr size_t off_stage = off_levels + sizeof(double2) * 4 * H;
+    static constexpr size_t off_a = off_stage + sizeof(double) * 2 * SW;
     static constexpr size_t a_doubles = (size_t)T2 * MB_DMAX + 2 + 32;   // + slack: a predicated-off read may be speculated
     static constexpr size_t bytes = off_a + sizeof(double) * a_doubles;
 };
+static_assert(MbLayout::off_stage % 16 == 0 && MbLayout::off_a % 16 == 0, "TMA destinations must be 16-byte aligned");
+static_assert(MbLayout::bytes <= 227 * 1024, "shared memory of one block");
 
-// values of window rows [f, e) -> shared memory by bulk copies (one thread); returns nothing, completion on `bar`.
-// The run starts at the even element q_al <= rowptr[f] (16-byte aligned source); an odd last element is moved by hand.
-__device__ __forceinline__ void mb_issue_window(const MpArgs& a, long long s0, int T2, double* smA, unsigned long long* bar) {
-    long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
-    const long long q0 = __ldg(a.rowptr + f), q1 = __ldg(a.rowptr + e);
+// Row pointer of a dense band in closed form (rowptr[0] = 0; k_band_dense verifies the operator's own array against it).
+__host__ __device__ __forceinline__ long long mb_rowptr(long long r, long long n, int bw) {
+    long long q = r * (2 * bw + 1);
+    const long long t = r < bw ? r : bw;                       // rows i < t lose bw - i entries at the top edge
+    q -= t * bw - t * (t - 1) / 2;
+    const long long m = r - (n - bw);                          // rows n - bw .. r - 1 lose 1 .. m entries at the bottom edge
+    if (m > 0) q -= m * (m + 1) / 2;
+    return q;
+}
+
+// Stage window rows [s0, s0 + T2): their values, and level 0 of both chains on [s0 - bw, s0 + T2 + bw) — one thread,
+// completion on `bar`.  Sources must be 16-byte aligned, so a run starts at the even element at or below its first one;
+// the copy may run one element past a run's end where the array goes on (it always does for the vectors: ld > n or n even).
+__device__ __forceinline__ void mb_issue_window(const MpArgs& a, int bw, long long s0, double* smA, double* stage,
+                                                unsigned long long* bar) {
+    constexpr int T2 = MbLayout::T2;
+    const long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
+    const long long q0 = mb_rowptr(f, a.n, bw), q1 = mb_rowptr(e, a.n, bw), nnz = mb_rowptr(a.n, a.n, bw);
     const long long q_al = q0 & ~1ll;
-    const long long cnt = q1 - q_al;
-    const unsigned bytes = (unsigned)((cnt & ~1ll) * 8);
-    if (cnt & 1) smA[cnt - 1] = __ldg(a.val + q1 - 1);
-    mbar_expect_tx(bar, bytes);                                // also the single arrival of this phase (bytes may be 0)
-    constexpr unsigned PIECE = 16384;
-    for (unsigned o = 0; o < bytes; o += PIECE)
-        bulk_g2s((char*)smA + o, (const char*)(a.val + q_al) + o, (bytes - o < PIECE) ? bytes - o : PIECE, bar);
-    // level 0 of that window and its row pointers -> L2, so that the top of the next window does not wait for DRAM
-    const long long g0 = (s0 - MB_PAD < 0 ? 0 : s0 - MB_PAD) & ~1ll;
-    long long g1 = s0 + T2 + MB_PAD > a.n ? a.n : s0 + T2 + MB_PAD;
-    g1 &= ~1ll;
-    if (g1 > g0 && (((unsigned long long)a.base0 | (unsigned long long)a.base1) & 15ull) == 0) {
-        const unsigned vb = (unsigned)((g1 - g0) * 8);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.base0 + g0), "r"(vb) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.base1 + g0), "r"(vb) : "memory");
+    long long cnt = q1 - q_al;
+    if (cnt & 1) {
+        if (q1 < nnz) ++cnt;                                   // the next row's first value: harmless, never read
+        else { smA[cnt - 1] = __ldg(a.val + q1 - 1); --cnt; }   // last window of the matrix
     }
+    const long long gs = s0 - bw < 0 ? 0 : s0 - bw, ge = s0 + T2 + bw > a.n ? a.n : s0 + T2 + bw;
+    const long long g_al = gs & ~1ll;
+    const long long gcnt = (ge - g_al + 1) & ~1ll;
+    const unsigned bytes_a = (unsigned)(cnt * 8), bytes_v = (unsigned)(gcnt * 8);
+    mbar_expect_tx(bar, bytes_a + 2u * bytes_v);               // also the single arrival of this phase
+    if (bytes_v) {
+        bulk_g2s(stage, a.base0 + g_al, bytes_v, bar);
+        bulk_g2s(stage + MbLayout::SW, a.base1 + g_al, bytes_v, bar);
+    }
+    constexpr unsigned PIECE = 16384;
+    for (unsigned o = 0; o < bytes_a; o += PIECE)
+        bulk_g2s((char*)smA + o, (const char*)(a.val + q_al) + o, (bytes_a - o < PIECE) ? bytes_a - o : PIECE, bar);
 }
 
 // BWT > 0: half bandwidth known at compile time (13: the 27-diagonal band of configs[3]) — the level loop is then
 // straight-line code (28 shared loads with immediate offsets, 108 multiplies, 108 adds) and the loads are scheduled ahead
 // of the arithmetic; BWT = 0 keeps bw a run-time value (uniform branches per position).
-template <int NT, int BWT>
-__global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
+template <int BWT>
+__global__ void __launch_bounds__(MB_NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
     if (pk_skip(ra)) return;
     const int k = a.dyn ? ra.st->k : a.k;
     if (k < 1) return;
-    using L = MbLayout<NT>;
-    constexpr int T2 = L::T2, H = L::H;
+    using L = MbLayout;
+    constexpr int NT = MB_NT, T2 = L::T2, H = L::H;
     const int bw = BWT ? BWT : a.bw;
     const int D = 2 * bw + 1;
     const int ghost = (k - 1) * bw;
@@ -233,6 +252,7 @@ __global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
     extern __shared__ __align__(16) unsigned char mb_raw[];
     unsigned long long* bar = (unsigned long long*)mb_raw;
     double2* lev = (double2*)(mb_raw + L::off_levels);          // [buffer 0..1][E | O][H], both chains interleaved per position
+    double* stage = (double*)(mb_raw + L::off_stage);           // level 0 as it lies in memory: [chain][SW]
     double* smA = (double*)(mb_raw + L::off_a);                 // the values of one window, as they lie in the CSR array
     const int tid = threadIdx.x;
     for (int i = tid; i < 4 * H; i += NT) lev[i] = make_double2(0.0, 0.0);
@@ -242,26 +262,18 @@ __global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
     }
     __syncthreads();
     const long long n_tiles = (a.n + t_out - 1) / t_out;
-    if (tid == 0 && blockIdx.x < n_tiles) mb_issue_window(a, (long long)blockIdx.x * t_out - ghost, T2, smA, bar);
+    if (tid == 0 && blockIdx.x < n_tiles) mb_issue_window(a, bw, (long long)blockIdx.x * t_out - ghost, smA, stage, bar);
     unsigned phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long o0 = tile * t_out;
         const long long o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
         const long long s0 = o0 - ghost;                // first row of the window (position 0)
         const long long rA = s0 + 2 * tid, rB = rA + 1;
-        // ---- where my two rows sit in the staged run
         const long long f = s0 < 0 ? 0 : s0;
-        const long long q_al = (long long)__ldg(a.rowptr + f) & ~1ll;
-        int qA = 0, cA = 0, qB = 0, cB = 0;
-        if (rA >= 0 && rA < a.n) {
-            const int q = __ldg(a.rowptr + rA), q2 = __ldg(a.rowptr + rA + 1);
-            qA = (int)(q - q_al); cA = q2 - q;
-            qB = (int)(q2 - q_al);                      // row B follows row A in the run
-        }
-        if (rB >= 0 && rB < a.n) {
-            if (rB == 0) qB = (int)(__ldg(a.rowptr + rB) - q_al);
-            cB = __ldg(a.rowptr + rB + 1) - (int)(qB + q_al);
-        }
+        const long long q_al = mb_rowptr(f, a.n, bw) & ~1ll;
+        const long long g_al = (s0 - bw < 0 ? 0 : s0 - bw) & ~1ll;
+        mbar_wait(bar, phase);
+        phase ^= 1u;
         // ---- level 0 of both chains; position p (row s0 + p) sits at index p + bw, even indices in E, odd in O: the
         // entries a thread gathers are then at the compile-time indices 2 tid + s, s = 0 .. 2 bw + 1
         double2* P = lev;
@@ -269,21 +281,40 @@ __global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
         for (int i = tid; i < T2 + 2 * bw; i += NT) {
             const long long g = s0 - bw + i;
             double u0 = 0.0, u1 = 0.0;
-            if (g >= 0 && g < a.n) { u0 = a.base0[g]; u1 = a.base1[g]; }
+            if (g >= 0 && g < a.n) { u0 = stage[g - g_al]; u1 = stage[L::SW + (g - g_al)]; }
             P[(i & 1) * H + (i >> 1)] = make_double2(u0, u1);
         }
         // ---- my two rows: shared memory -> registers (diagonal d of row r is its entry d - max(bw - r, 0))
-        mbar_wait(bar, phase);
-        phase ^= 1u;
         double vA[MB_DMAX], vB[MB_DMAX];
-        if (s0 >= bw && s0 + T2 + bw <= a.n) {          // window clear of the matrix edges: every row is full
-            const double* sA = smA + qA;
+        const bool interior = s0 >= bw && s0 + T2 + bw <= a.n;      // window clear of the matrix edges: every row is full
+        if (BWT && interior) {
+            // the pair of rows is 2 D consecutive doubles from q = (first value of the window) + 2 tid D
+            double w[2 * MB_DMAX];
+            const int q = (int)(mb_rowptr(s0, a.n, bw) - q_al) + 2 * tid * (2 * BWT + 1);
+            if ((q & 1) == 0) {
+                const double2* s2 = (const double2*)(smA + q);
+#pragma unroll
+                for (int j = 0; j < MB_DMAX; ++j) { const double2 t2 = s2[j]; w[2 * j] = t2.x; w[2 * j + 1] = t2.y; }
+            } else {
+                const double2* s2 = (const double2*)(smA + q + 1);
+                w[0] = smA[q];
+#pragma unroll
+                for (int j = 0; j < MB_DMAX - 1; ++j) { const double2 t2 = s2[j]; w[2 * j + 1] = t2.x; w[2 * j + 2] = t2.y; }
+                w[2 * MB_DMAX - 1] = smA[q + 2 * MB_DMAX - 1];
+            }
+#pragma unroll
+            for (int d = 0; d < MB_DMAX; ++d) { vA[d] = w[d]; vB[d] = w[MB_DMAX + d]; }
+        } else if (interior) {
+            const double* sA = smA + (int)(mb_rowptr(s0, a.n, bw) - q_al) + 2 * tid * D;
 #pragma unroll
             for (int d = 0; d < MB_DMAX; ++d) {
                 if (d < D) { vA[d] = sA[d]; vB[d] = sA[D + d]; }
                 else { vA[d] = 0.0; vB[d] = 0.0; }
             }
         } else {
+            int qA = 0, cA = 0, qB = 0, cB = 0;
+            if (rA >= 0 && rA < a.n) { const long long q = mb_rowptr(rA, a.n, bw); qA = (int)(q - q_al); cA = (int)(mb_rowptr(rA + 1, a.n, bw) - q); }
+            if (rB >= 0 && rB < a.n) { const long long q = mb_rowptr(rB, a.n, bw); qB = (int)(q - q_al); cB = (int)(mb_rowptr(rB + 1, a.n, bw) - q); }
             const int dA = rA < bw ? (int)(bw - rA) : 0, dB = rB < bw ? (int)(bw - rB) : 0;
 #pragma unroll
             for (int d = 0; d < MB_DMAX; ++d) {
@@ -292,9 +323,9 @@ __global__ void __launch_bounds__(NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra) {
                 vB[d] = (eB >= 0 && eB < cB) ? smA[qB + eB] : 0.0;
             }
         }
-        __syncthreads();                                // level 0 visible; everyone is done with the staged values
+        __syncthreads();                                // level 0 visible; everyone is done with the staged window
         if (tid == 0 && tile + gridDim.x < n_tiles)     // the next window of this block streams in behind the levels
-            mb_issue_window(a, (tile + gridDim.x) * t_out - ghost, T2, smA, bar);
+            mb_issue_window(a, bw, (tile + gridDim.x) * t_out - ghost, smA, stage, bar);
         // my rows' own positions: index 2 tid + bw (row A) and 2 tid + bw + 1 (row B)
         const int wA = ((bw & 1) ? H : 0) + tid + (bw >> 1);
         const int wB = (((bw + 1) & 1) ? H : 0) + tid + ((bw + 1) >> 1);
@@ -338,7 +369,7 @@ __global__ void k_band_dense(const int32_t* __restrict__ rowptr, const int32_t* 
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
         const long long lo = r - bw < 0 ? 0 : r - bw, hi = r + bw > n - 1 ? n - 1 : r + bw;
         const int q0 = rowptr[r], q1 = rowptr[r + 1];
-        if (q1 - q0 != (int)(hi - lo + 1)) bad = 1;
+        if (q1 - q0 != (int)(hi - lo + 1) || q0 != mb_rowptr(r, n, bw) || q1 != mb_rowptr(r + 1, n, bw)) bad = 1;
         else
             for (int q = q0; q < q1; ++q)
                 if (col[q] != (int)(lo + (q - q0))) { bad = 1; break; }
@@ -428,15 +459,6 @@ static int band_info(pk_ctx* ctx, pk_mat* m) {
 }
 
 // Window of the kernel that will run: rows per block, before the trapezoid is taken off.
-static int band_threads() {
-    static int nt = -1;
-    if (nt < 0) {
-        const char* e = getenv("PK_MATPOW_NT");
-        nt = e ? atoi(e) : 448;
-        if (nt != 384 && nt != 448) nt = 448;
-    }
-    return nt;
-}
 static bool band_kernel_on(const pk_mat* m) {
     static int enabled = -1;
     if (enabled < 0) {
@@ -445,7 +467,7 @@ static bool band_kernel_on(const pk_mat* m) {
     }
     return enabled && m->mp_dense && !m->distributed;
 }
-static int mp_window(const pk_mat* m) { return band_kernel_on(m) ? 2 * band_threads() : MP_T; }
+static int mp_window(const pk_mat* m) { return band_kernel_on(m) ? MbLayout::T2 : MP_T; }
 
 extern "C" int pk_mat_set_matpow_ext(pk_mat* m, int half_bw, int max_row_nnz, int64_t row0, int64_t n_global,
                                      const int64_t* d_halo_global, int64_t rows_above, const int32_t* d_rowptr_above,
@@ -533,20 +555,19 @@ int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1
     ra.dyn_cj = -1;
     ra.dyn_last = 0;
     if (band_kernel_on(m)) {
-        const int nt = band_threads();
-        const size_t smem = nt == 384 ? MbLayout<384>::bytes : MbLayout<448>::bytes;
+        if ((((uintptr_t)base0 | (uintptr_t)base1) & 15) != 0) {
+            pk_set_error("matrix powers on a dense band stage level 0 by TMA: the level vectors must be 16-byte aligned");
+            return PK_ERR_ARG;
+        }
+        const size_t smem = MbLayout::bytes;
         const bool b13 = a.bw == 13;
-        const void* kb = nt == 384 ? (b13 ? (const void*)k_matpow_band<384, 13> : (const void*)k_matpow_band<384, 0>)
-                                   : (b13 ? (const void*)k_matpow_band<448, 13> : (const void*)k_matpow_band<448, 0>);
-        pk_blocks_per_sm(kb, nt, smem);              // opts in to the dynamic shared memory size
-        const int t_out = 2 * nt - 2 * (k - 1) * a.bw;
+        pk_blocks_per_sm(b13 ? (const void*)k_matpow_band<13> : (const void*)k_matpow_band<0>, MB_NT, smem);   // opt in to the size
+        const int t_out = MbLayout::T2 - 2 * (k - 1) * a.bw;
         const long long n_tiles = (a.n + t_out - 1) / t_out;
         int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
         if (grid < 1) grid = 1;
-        if (nt == 384 && b13) k_matpow_band<384, 13><<<grid, 384, smem, ctx->stream>>>(a, ra);
-        else if (nt == 384) k_matpow_band<384, 0><<<grid, 384, smem, ctx->stream>>>(a, ra);
-        else if (b13) k_matpow_band<448, 13><<<grid, 448, smem, ctx->stream>>>(a, ra);
-        else k_matpow_band<448, 0><<<grid, 448, smem, ctx->stream>>>(a, ra);
+        if (b13) k_matpow_band<13><<<grid, MB_NT, smem, ctx->stream>>>(a, ra);
+        else k_matpow_band<0><<<grid, MB_NT, smem, ctx->stream>>>(a, ra);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             pk_set_error("matrix-powers (dense band) launch: %s", cudaGetErrorString(e));
@@ -591,7 +612,7 @@ extern "C" int pk_matpow(pk_ctx* ctx, pk_mat* mat, int k, double* d_base0, doubl
     PK_CUDA(cudaSetDevice(ctx->device));
     if (!pk_matpow_ok(ctx, mat, k < 2 ? 2 : k)) {
         pk_set_error("operator not eligible for the one-pass matrix-powers kernel (needs a square single-GPU CSR block, "
-                     "rows of <= %d nonzeros, half bandwidth bw with W - 2(k-1)bw >= W/2 for the window W = 640 rows, or 1024 "
+                     "rows of <= %d nonzeros, half bandwidth bw with W - 2(k-1)bw >= W/2 for the window W = 640 rows, or 768 "
                      "for a dense band; PK_MATPOW=0 disables it)", MP_RMAX);
         return PK_ERR_UNSUPPORTED;
     }

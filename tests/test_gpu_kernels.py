@@ -225,7 +225,7 @@ def _band_with_holes(n, half_bw, seed):
 
 @pytest.mark.parametrize("n,half_bw,k,structure", [
     (30011, 13, 8, "dense"), (5000, 2, 4, "dense"), (700, 13, 2, "dense"), (100003, 13, 5, "dense"),
-    (27, 13, 2, "dense"), (1024, 13, 8, "dense"), (843, 13, 8, "dense"), (4099, 1, 8, "dense"), (60013, 13, 16, "dense"),
+    (27, 13, 2, "dense"), (1024, 13, 8, "dense"), (843, 13, 8, "dense"), (4099, 1, 8, "dense"), (60013, 13, 15, "dense"),
     (200003, 6, 12, "dense"),
     (30011, 13, 8, "holes"), (5000, 2, 4, "holes"), (700, 13, 2, "holes"), (100003, 13, 5, "holes")])
 def test_matrix_powers_one_pass_is_bitwise_k_sequential_spmvs(pk, n, half_bw, k, structure):

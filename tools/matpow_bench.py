@@ -1,9 +1,9 @@
 """Time the one-pass matrix-powers kernel and a k-skip MrR solve on the banded system of BASELINE.json configs[3]
 (n = 2^25, 27 diagonals, k = 8) (kernel: host clock around synchronised groups of launches; solve: CUDA events).  The kernel variant is chosen by environment variables read once per
-process (PK_MATPOW_BAND, PK_MATPOW_NT, PK_MATPOW_PREFETCH, PK_MATPOW), so run one process per variant:
+process (PK_MATPOW_BAND, PK_MATPOW), so run one process per variant:
 
     PK_MATPOW_BAND=0 python tools/matpow_bench.py      # general kernel (one row per thread)
-    python tools/matpow_bench.py                       # dense-band kernel (two rows per thread), 512 threads
+    python tools/matpow_bench.py                       # dense-band kernel (two rows per thread)
 """
 import json
 import os
@@ -24,7 +24,7 @@ def main():
     op = Operator.from_csr_tensors(rp, col, val, n, ctx)
     b = dp.hash_normal(0, n, offset=0, ctx=ctx)
     ld = op.ld
-    out = {"n": n, "bw": bw, "k": k, "env": {e: os.environ.get(e) for e in ("PK_MATPOW", "PK_MATPOW_BAND", "PK_MATPOW_NT", "PK_MATPOW_PREFETCH")}}
+    out = {"n": n, "bw": bw, "k": k, "env": {e: os.environ.get(e) for e in ("PK_MATPOW", "PK_MATPOW_BAND")}}
     if os.environ.get("PK_MATPOW", "1") not in ("0", ""):
         out["kernel"] = op.matpow_info(k)
         U = torch.zeros((k + 1) * ld, dtype=torch.float64, device="cuda")
@@ -42,7 +42,7 @@ def main():
         ctx.sync()
         out["matpow_ms"] = (time.perf_counter() - t0) * 1e3 / 5
         nnz = int(val.numel())
-        out["matpow_algorithmic_gb"] = (8.0 * nnz + 4.0 * (n + 1) + (2 + 2 * k) * 8.0 * n) / 1e9
+        out["matpow_algorithmic_gb"] = ((8.0 * nnz if out["kernel"]["kernel"] == "dense-band" else 12.0 * nnz + 4.0 * (n + 1)) + (2 + 2 * k) * 8.0 * n) / 1e9
         out["matpow_gbs"] = out["matpow_algorithmic_gb"] / (out["matpow_ms"] * 1e-3)
         del U, V
     x, info = solve("kskipmrr", op, b, tol=1e-8, maxiter=400, use_graph=True, ctx=ctx, k=k)      # warm-up
