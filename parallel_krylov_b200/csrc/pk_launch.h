@@ -54,6 +54,9 @@ int pk_tile_max_nnz(pk_ctx* ctx, const int32_t* rowptr, long long n_rows, int ti
 // pk_matpow.cu — k levels of both basis chains in one pass over A (small-bandwidth operators)
 bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k);
 int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn);
+bool pk_mrr_steps_ok(pk_ctx* ctx, pk_mat* m, int k);
+int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, double* y, double* z, double* x,
+                        double* t0, double* t1, double* t2, int epi);
 
 // pk_persistent.cu — whole CG loop as one cooperative kernel (small, L2-resident systems)
 int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double* p, double* v, int iters);

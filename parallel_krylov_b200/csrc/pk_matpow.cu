@@ -207,32 +207,95 @@ __host__ __device__ __forceinline__ long long mb_rowptr(long long r, long long n
     return q;
 }
 
+// The values of window rows [s0, s0 + T2) as one run of the CSR value array: source (16-byte aligned: the run starts at
+// the even element at or below its first one) and byte count (a multiple of 16; an odd last element of the MATRIX is moved
+// by hand, elsewhere the copy simply takes the next row's first value along).
+__device__ __forceinline__ void mb_value_run(const double* val, long long n, int bw, long long s0, double* smA,
+                                             const double** src, unsigned* bytes) {
+    constexpr int T2 = MbLayout::T2;
+    const long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > n ? n : s0 + T2;
+    const long long q0 = mb_rowptr(f, n, bw), q1 = mb_rowptr(e, n, bw), nnz = mb_rowptr(n, n, bw);
+    const long long q_al = q0 & ~1ll;
+    long long cnt = q1 - q_al;
+    if (cnt & 1) {
+        if (q1 < nnz) ++cnt;
+        else { smA[cnt - 1] = __ldg(val + q1 - 1); --cnt; }
+    }
+    *src = val + q_al;
+    *bytes = (unsigned)(cnt * 8);
+}
+__device__ __forceinline__ void mb_copy_values(double* smA, const double* src, unsigned bytes, unsigned long long* bar) {
+    constexpr unsigned PIECE = 16384;
+    for (unsigned o = 0; o < bytes; o += PIECE)
+        bulk_g2s((char*)smA + o, (const char*)src + o, (bytes - o < PIECE) ? bytes - o : PIECE, bar);
+}
+
 // Stage window rows [s0, s0 + T2): their values, and level 0 of both chains on [s0 - bw, s0 + T2 + bw) — one thread,
 // completion on `bar`.  Sources must be 16-byte aligned, so a run starts at the even element at or below its first one;
 // the copy may run one element past a run's end where the array goes on (it always does for the vectors: ld > n or n even).
 __device__ __forceinline__ void mb_issue_window(const MpArgs& a, int bw, long long s0, double* smA, double* stage,
                                                 unsigned long long* bar) {
     constexpr int T2 = MbLayout::T2;
-    const long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
-    const long long q0 = mb_rowptr(f, a.n, bw), q1 = mb_rowptr(e, a.n, bw), nnz = mb_rowptr(a.n, a.n, bw);
-    const long long q_al = q0 & ~1ll;
-    long long cnt = q1 - q_al;
-    if (cnt & 1) {
-        if (q1 < nnz) ++cnt;                                   // the next row's first value: harmless, never read
-        else { smA[cnt - 1] = __ldg(a.val + q1 - 1); --cnt; }   // last window of the matrix
-    }
+    unsigned bytes_a;
+    const double* src_a;
+    mb_value_run(a.val, a.n, bw, s0, smA, &src_a, &bytes_a);
     const long long gs = s0 - bw < 0 ? 0 : s0 - bw, ge = s0 + T2 + bw > a.n ? a.n : s0 + T2 + bw;
     const long long g_al = gs & ~1ll;
     const long long gcnt = (ge - g_al + 1) & ~1ll;
-    const unsigned bytes_a = (unsigned)(cnt * 8), bytes_v = (unsigned)(gcnt * 8);
+    const unsigned bytes_v = (unsigned)(gcnt * 8);
     mbar_expect_tx(bar, bytes_a + 2u * bytes_v);               // also the single arrival of this phase
     if (bytes_v) {
         bulk_g2s(stage, a.base0 + g_al, bytes_v, bar);
         bulk_g2s(stage + MbLayout::SW, a.base1 + g_al, bytes_v, bar);
     }
-    constexpr unsigned PIECE = 16384;
-    for (unsigned o = 0; o < bytes_a; o += PIECE)
-        bulk_g2s((char*)smA + o, (const char*)(a.val + q_al) + o, (bytes_a - o < PIECE) ? bytes_a - o : PIECE, bar);
+    mb_copy_values(smA, src_a, bytes_a, bar);
+}
+
+// My two rows (s0 + 2 tid, s0 + 2 tid + 1) of a staged window: shared memory -> registers.  Diagonal d of row r is its
+// entry d - max(bw - r, 0); entries clipped by the matrix edges become +0.0.
+template <int BWT>
+__device__ __forceinline__ void mb_rows_to_regs(const double* smA, long long s0, long long q_al, int tid, long long n,
+                                                int bw, double (&vA)[MB_DMAX], double (&vB)[MB_DMAX]) {
+    constexpr int T2 = MbLayout::T2;
+    const int D = 2 * bw + 1;
+    const long long rA = s0 + 2 * tid, rB = rA + 1;
+    const bool interior = s0 >= bw && s0 + T2 + bw <= n;           // window clear of the matrix edges: every row is full
+    if (BWT && interior) {
+        // the pair of rows is 2 D consecutive doubles from q = (first value of the window) + 2 tid D
+        double w[2 * MB_DMAX];
+        const int q = (int)(mb_rowptr(s0, n, bw) - q_al) + 2 * tid * (2 * BWT + 1);
+        if ((q & 1) == 0) {
+            const double2* s2 = (const double2*)(smA + q);
+#pragma unroll
+            for (int j = 0; j < MB_DMAX; ++j) { const double2 t2 = s2[j]; w[2 * j] = t2.x; w[2 * j + 1] = t2.y; }
+        } else {
+            const double2* s2 = (const double2*)(smA + q + 1);
+            w[0] = smA[q];
+#pragma unroll
+            for (int j = 0; j < MB_DMAX - 1; ++j) { const double2 t2 = s2[j]; w[2 * j + 1] = t2.x; w[2 * j + 2] = t2.y; }
+            w[2 * MB_DMAX - 1] = smA[q + 2 * MB_DMAX - 1];
+        }
+#pragma unroll
+        for (int d = 0; d < MB_DMAX; ++d) { vA[d] = w[d]; vB[d] = w[MB_DMAX + d]; }
+    } else if (interior) {
+        const double* sA = smA + (int)(mb_rowptr(s0, n, bw) - q_al) + 2 * tid * D;
+#pragma unroll
+        for (int d = 0; d < MB_DMAX; ++d) {
+            if (d < D) { vA[d] = sA[d]; vB[d] = sA[D + d]; }
+            else { vA[d] = 0.0; vB[d] = 0.0; }
+        }
+    } else {
+        int qA = 0, cA = 0, qB = 0, cB = 0;
+        if (rA >= 0 && rA < n) { const long long q = mb_rowptr(rA, n, bw); qA = (int)(q - q_al); cA = (int)(mb_rowptr(rA + 1, n, bw) - q); }
+        if (rB >= 0 && rB < n) { const long long q = mb_rowptr(rB, n, bw); qB = (int)(q - q_al); cB = (int)(mb_rowptr(rB + 1, n, bw) - q); }
+        const int dA = rA < bw ? (int)(bw - rA) : 0, dB = rB < bw ? (int)(bw - rB) : 0;
+#pragma unroll
+        for (int d = 0; d < MB_DMAX; ++d) {
+            const int eA = d - dA, eB = d - dB;
+            vA[d] = (eA >= 0 && eA < cA) ? smA[qA + eA] : 0.0;
+            vB[d] = (eB >= 0 && eB < cB) ? smA[qB + eB] : 0.0;
+        }
+    }
 }
 
 // BWT > 0: half bandwidth known at compile time (13: the 27-diagonal band of configs[3]) — the level loop is then
@@ -284,45 +347,9 @@ __global__ void __launch_bounds__(MB_NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra
             if (g >= 0 && g < a.n) { u0 = stage[g - g_al]; u1 = stage[L::SW + (g - g_al)]; }
             P[(i & 1) * H + (i >> 1)] = make_double2(u0, u1);
         }
-        // ---- my two rows: shared memory -> registers (diagonal d of row r is its entry d - max(bw - r, 0))
+        // ---- my two rows: shared memory -> registers
         double vA[MB_DMAX], vB[MB_DMAX];
-        const bool interior = s0 >= bw && s0 + T2 + bw <= a.n;      // window clear of the matrix edges: every row is full
-        if (BWT && interior) {
-            // the pair of rows is 2 D consecutive doubles from q = (first value of the window) + 2 tid D
-            double w[2 * MB_DMAX];
-            const int q = (int)(mb_rowptr(s0, a.n, bw) - q_al) + 2 * tid * (2 * BWT + 1);
-            if ((q & 1) == 0) {
-                const double2* s2 = (const double2*)(smA + q);
-#pragma unroll
-                for (int j = 0; j < MB_DMAX; ++j) { const double2 t2 = s2[j]; w[2 * j] = t2.x; w[2 * j + 1] = t2.y; }
-            } else {
-                const double2* s2 = (const double2*)(smA + q + 1);
-                w[0] = smA[q];
-#pragma unroll
-                for (int j = 0; j < MB_DMAX - 1; ++j) { const double2 t2 = s2[j]; w[2 * j + 1] = t2.x; w[2 * j + 2] = t2.y; }
-                w[2 * MB_DMAX - 1] = smA[q + 2 * MB_DMAX - 1];
-            }
-#pragma unroll
-            for (int d = 0; d < MB_DMAX; ++d) { vA[d] = w[d]; vB[d] = w[MB_DMAX + d]; }
-        } else if (interior) {
-            const double* sA = smA + (int)(mb_rowptr(s0, a.n, bw) - q_al) + 2 * tid * D;
-#pragma unroll
-            for (int d = 0; d < MB_DMAX; ++d) {
-                if (d < D) { vA[d] = sA[d]; vB[d] = sA[D + d]; }
-                else { vA[d] = 0.0; vB[d] = 0.0; }
-            }
-        } else {
-            int qA = 0, cA = 0, qB = 0, cB = 0;
-            if (rA >= 0 && rA < a.n) { const long long q = mb_rowptr(rA, a.n, bw); qA = (int)(q - q_al); cA = (int)(mb_rowptr(rA + 1, a.n, bw) - q); }
-            if (rB >= 0 && rB < a.n) { const long long q = mb_rowptr(rB, a.n, bw); qB = (int)(q - q_al); cB = (int)(mb_rowptr(rB + 1, a.n, bw) - q); }
-            const int dA = rA < bw ? (int)(bw - rA) : 0, dB = rB < bw ? (int)(bw - rB) : 0;
-#pragma unroll
-            for (int d = 0; d < MB_DMAX; ++d) {
-                const int eA = d - dA, eB = d - dB;
-                vA[d] = (eA >= 0 && eA < cA) ? smA[qA + eA] : 0.0;
-                vB[d] = (eB >= 0 && eB < cB) ? smA[qB + eB] : 0.0;
-            }
-        }
+        mb_rows_to_regs<BWT>(smA, s0, q_al, tid, a.n, bw, vA, vB);
         __syncthreads();                                // level 0 visible; everyone is done with the staged window
         if (tid == 0 && tile + gridDim.x < n_tiles)     // the next window of this block streams in behind the levels
             mb_issue_window(a, bw, (tile + gridDim.x) * t_out - ghost, smA, stage, bar);
@@ -361,6 +388,184 @@ __global__ void __launch_bounds__(MB_NT, 1) k_matpow_band(MpArgs a, PkRedArgs ra
             double2* t0 = P; P = N; N = t0;
         }
     }
+}
+
+// ---- the k+1 steps of a k-skip MrR trip in ONE pass over a dense band -------------------------------------------------
+// Once the Gram epilogue has produced (zeta_j, eta_j), j = 0..k, the steps of a trip (/root/reference/v3/cpu/kskipmrr.py:
+// 63-69 and :87-93) are a fixed recurrence with no inner product in it:
+//     y <- eta_j y + zeta_j (A r);   z <- eta_j z - zeta_j r;   r <- r - y;   x <- x - z;   (A r) <- A r
+// — k+1 element-wise updates, each followed by ONE mat-vec of r.  The step-by-step path streams A through the SpMV
+// kernel k+1 times per trip (17 of the 25 ms of a trip on the 32M band); here a block keeps the rows of A of its window
+// in registers (as k_matpow_band does), r of the window ping-pongs through shared memory between the steps, and y, z, x,
+// A r of a thread's two rows never leave its registers: A and the five vectors are read once and written once per trip.
+// After m mat-vecs the window is valid (m bw) rows inside either end, so a window of 768 rows finishes
+// 768 - 2 (k+1) bw of them.  Every row runs exactly the arithmetic of k_mrr_update / the fused SpMV epilogue
+// (same products, same sums, same order), so x, r, y, z come out bit-identical to the step-by-step path.
+// Windows overlap, hence r, A r, y are written to scratch vectors (the neighbours still read the old ones) and copied
+// home by k_copy3; z and x are only touched on the rows a block finishes, in place.
+struct StArgs {
+    const double* val;
+    long long n;
+    int bw, k;
+    const double* r; const double* ar; const double* y;         // read on whole windows
+    double* z; double* x;                                       // in place, finished rows only
+    double* r_out; double* ar_out; double* y_out;
+};
+
+struct StLayout {
+    static constexpr int T2 = MbLayout::T2, H = MbLayout::H;
+    static constexpr int SW = T2 + 2;                           // doubles per staged vector run (even)
+    static constexpr size_t off_coef = 16;                      // after the mbarrier: (zeta_j, eta_j), j = 0..PK_KMAX
+    static constexpr size_t off_levels = off_coef + sizeof(double) * 2 * (PK_KMAX + 1) + 16;
+    static constexpr size_t off_stage = off_levels + sizeof(double) * 4 * H;      // [buffer 0..1][E | O][H]
+    static constexpr size_t off_a = off_stage + sizeof(double) * 5 * SW;          // r, A r, y (window), z, x (finished rows)
+    static constexpr size_t bytes = off_a + sizeof(double) * MbLayout::a_doubles;
+};
+static_assert(StLayout::off_levels % 16 == 0 && StLayout::off_stage % 16 == 0 && StLayout::off_a % 16 == 0, "alignment");
+static_assert(StLayout::bytes <= 227 * 1024, "shared memory of one block");
+
+__device__ __forceinline__ void st_issue_window(const StArgs& a, int bw, long long s0, long long o0, long long o1,
+                                                double* smA, double* stage, unsigned long long* bar) {
+    constexpr int T2 = StLayout::T2, SW = StLayout::SW;
+    unsigned bytes_a;
+    const double* src_a;
+    mb_value_run(a.val, a.n, bw, s0, smA, &src_a, &bytes_a);
+    const long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
+    const long long w_al = f & ~1ll, o_al = o0 & ~1ll;
+    // r, A r, y live in ld-padded work vectors: a run may take one element past its end along.  x is the caller's
+    // solution vector of exactly n entries: an odd last element of it (and of z, for symmetry) is moved by hand.
+    const unsigned bytes_w = (unsigned)(((e - w_al + 1) & ~1ll) * 8);
+    long long ocnt = o1 - o_al;
+    if (ocnt & 1) {
+        if (o1 < a.n) ++ocnt;
+        else { stage[3 * SW + ocnt - 1] = a.z[o1 - 1]; stage[4 * SW + ocnt - 1] = a.x[o1 - 1]; --ocnt; }
+    }
+    const unsigned bytes_o = (unsigned)(ocnt * 8);
+    mbar_expect_tx(bar, bytes_a + 3u * bytes_w + 2u * bytes_o);
+    bulk_g2s(stage, a.r + w_al, bytes_w, bar);
+    bulk_g2s(stage + SW, a.ar + w_al, bytes_w, bar);
+    bulk_g2s(stage + 2 * SW, a.y + w_al, bytes_w, bar);
+    if (bytes_o) {
+        bulk_g2s(stage + 3 * SW, a.z + o_al, bytes_o, bar);
+        bulk_g2s(stage + 4 * SW, a.x + o_al, bytes_o, bar);
+    }
+    mb_copy_values(smA, src_a, bytes_a, bar);
+}
+
+template <int BWT>
+__global__ void __launch_bounds__(MB_NT, 1) k_mrr_steps_band(StArgs a, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    using L = StLayout;
+    constexpr int NT = MB_NT, T2 = L::T2, H = L::H, SW = L::SW;
+    const int k = a.k;
+    const int bw = BWT ? BWT : a.bw;
+    const int D = 2 * bw + 1;
+    const int ghost = (k + 1) * bw;                     // k+1 mat-vecs per trip (k between the steps + the closing one)
+    const int t_out = T2 - 2 * ghost;
+    extern __shared__ __align__(16) unsigned char mb_raw[];
+    unsigned long long* bar = (unsigned long long*)mb_raw;
+    double* coef = (double*)(mb_raw + L::off_coef);
+    double* lev = (double*)(mb_raw + L::off_levels);
+    double* stage = (double*)(mb_raw + L::off_stage);
+    double* smA = (double*)(mb_raw + L::off_a);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * H; i += NT) lev[i] = 0.0;
+    for (int i = tid; i < 2 * (k + 1); i += NT) coef[i] = ra.st->coef[i];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n_tiles = (a.n + t_out - 1) / t_out;
+    auto issue = [&](long long tile) {
+        const long long o0 = tile * t_out, o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
+        st_issue_window(a, bw, o0 - ghost, o0, o1, smA, stage, bar);
+    };
+    if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x);
+    unsigned phase = 0;
+    double acc[1] = {0.0};
+    // my rows' own positions in a level: index 2 tid + bw (row A) and 2 tid + bw + 1 (row B); even indices in E, odd in O
+    const int wA = ((bw & 1) ? H : 0) + tid + (bw >> 1);
+    const int wB = (((bw + 1) & 1) ? H : 0) + tid + ((bw + 1) >> 1);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long o0 = tile * t_out;
+        const long long o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
+        const long long s0 = o0 - ghost;
+        const long long rowA = s0 + 2 * tid, rowB = rowA + 1;
+        const long long f = s0 < 0 ? 0 : s0;
+        const long long q_al = mb_rowptr(f, a.n, bw) & ~1ll;
+        const long long w_al = f & ~1ll, o_al = o0 & ~1ll;
+        const bool inA = rowA >= 0 && rowA < a.n, inB = rowB >= 0 && rowB < a.n;
+        const bool outA = rowA >= o0 && rowA < o1, outB = rowB >= o0 && rowB < o1;
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        double rA = 0.0, arA = 0.0, yA = 0.0, zA = 0.0, xA = 0.0, rB = 0.0, arB = 0.0, yB = 0.0, zB = 0.0, xB = 0.0;
+        if (inA) { rA = stage[rowA - w_al]; arA = stage[SW + (rowA - w_al)]; yA = stage[2 * SW + (rowA - w_al)]; }
+        if (inB) { rB = stage[rowB - w_al]; arB = stage[SW + (rowB - w_al)]; yB = stage[2 * SW + (rowB - w_al)]; }
+        if (outA) { zA = stage[3 * SW + (rowA - o_al)]; xA = stage[4 * SW + (rowA - o_al)]; }
+        if (outB) { zB = stage[3 * SW + (rowB - o_al)]; xB = stage[4 * SW + (rowB - o_al)]; }
+        double vA[MB_DMAX], vB[MB_DMAX];
+        mb_rows_to_regs<BWT>(smA, s0, q_al, tid, a.n, bw, vA, vB);
+        __syncthreads();                                // everyone is done with the staged window (and with the levels)
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x);
+        int cur = 0;
+        for (int j = 0; j <= k; ++j) {
+            const double zeta = coef[2 * j], eta = coef[2 * j + 1];
+            // the step, exactly as k_mrr_update / the FUSE == 1 epilogue of k_spmv_tma write it
+            yA = eta * yA + zeta * arA;
+            zA = eta * zA - zeta * rA;
+            rA = rA - yA;
+            xA = xA - zA;
+            yB = eta * yB + zeta * arB;
+            zB = eta * zB - zeta * rB;
+            rB = rB - yB;
+            xB = xB - zB;
+            double* Nb = lev + cur * 2 * H;
+            Nb[wA] = rA;
+            Nb[wB] = rB;
+            __syncthreads();
+            // A r of my two rows from the r just published (entries 2 tid - bw + s, s = 0 .. 2 bw + 1)
+            double sA = 0.0, sB = 0.0;
+            const double* Pt = Nb + tid;
+#pragma unroll
+            for (int s = 0; s <= MB_DMAX; ++s) {
+                if (s > D) break;
+                const double X = Pt[(s & 1) * H + (s >> 1)];
+                if (s < MB_DMAX) {
+                    if (s < D) sA += vA[s] * X;
+                }
+                if (s >= 1) sB += vB[s - 1] * X;
+            }
+            arA = sA;
+            arB = sB;
+            cur ^= 1;
+        }
+        if (outA) {
+            a.r_out[rowA] = rA; a.ar_out[rowA] = arA; a.y_out[rowA] = yA; a.z[rowA] = zA; a.x[rowA] = xA;
+            acc[0] += rA * rA;
+        }
+        if (outB) {
+            a.r_out[rowB] = rB; a.ar_out[rowB] = arB; a.y_out[rowB] = yB; a.z[rowB] = zB; a.x[rowB] = xB;
+            acc[0] += rB * rB;
+        }
+    }
+    pk_grid_reduce<1, MB_NT>(acc, ra);
+}
+
+// three vectors home in one launch (128-bit when everything is 16-byte aligned)
+__global__ void __launch_bounds__(256) k_copy3(long long n, const double* __restrict__ s0, double* __restrict__ d0,
+                                               const double* __restrict__ s1, double* __restrict__ d1,
+                                               const double* __restrict__ s2, double* __restrict__ d2, PkRedArgs ra) {
+    if (pk_skip(ra)) return;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n2 = n >> 1;
+    const double2 *a0 = (const double2*)s0, *a1 = (const double2*)s1, *a2 = (const double2*)s2;
+    double2 *b0 = (double2*)d0, *b1 = (double2*)d1, *b2 = (double2*)d2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 u = a0[i], v = a1[i], w = a2[i];
+        b0[i] = u; b1[i] = v; b2[i] = w;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { d0[n - 1] = s0[n - 1]; d1[n - 1] = s1[n - 1]; d2[n - 1] = s2[n - 1]; }
 }
 
 // Is the block a dense band of half width bw?  out[0] counts the rows that are not.
@@ -593,6 +798,74 @@ int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1
     }
     ctx->launches++;
     ctx->spmvs += 2LL * k;
+    return PK_OK;
+}
+
+// Can the k+1 steps of a k-skip MrR trip run as one pass (k_mrr_steps_band)?  Dense band on one GPU, and the window must
+// keep at least half of its rows after k+1 mat-vecs.
+bool pk_mrr_steps_ok(pk_ctx* ctx, pk_mat* m, int k) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PK_KSTEPS");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || k < 2 || !pk_matpow_ok(ctx, m, k) || !band_kernel_on(m)) return false;
+    return MbLayout::T2 - 2 * (k + 1) * m->mp_bw >= MbLayout::T2 / 2;
+}
+
+// r, ar = A r, y, z, x: the vectors of the trip; t0..t2: three scratch vectors (free basis slots).  Runs the k+1 steps,
+// the closing mat-vec and the trip-end epilogue (red[0] = r.r); leaves everything at home.
+int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, double* y, double* z, double* x,
+                        double* t0, double* t1, double* t2, int epi) {
+    const uintptr_t al = (uintptr_t)r | (uintptr_t)ar | (uintptr_t)y | (uintptr_t)z | (uintptr_t)x | (uintptr_t)t0 | (uintptr_t)t1 | (uintptr_t)t2;
+    if (al & 15) {
+        pk_set_error("fused k-skip steps stage their vectors by TMA: all vectors must be 16-byte aligned");
+        return PK_ERR_ARG;
+    }
+    StArgs a{};
+    a.val = m->val; a.n = m->n_rows; a.bw = m->mp_bw; a.k = k;
+    a.r = r; a.ar = ar; a.y = y; a.z = z; a.x = x;
+    a.r_out = t0; a.ar_out = t1; a.y_out = t2;
+    PkRedArgs ra{};
+    ra.partials = ctx->red.partials;
+    ra.ticket = ctx->red.ticket;
+    ra.max_blocks = ctx->red.max_blocks;
+    ra.st = ctx->d_state;
+    ra.epi = epi;
+    ra.g_off = -1;
+    ra.only_rollback = ctx->ctl_only_rollback;
+    ra.dyn_cj = -1;
+    const size_t smem = StLayout::bytes;
+    const bool b13 = a.bw == 13;
+    pk_blocks_per_sm(b13 ? (const void*)k_mrr_steps_band<13> : (const void*)k_mrr_steps_band<0>, MB_NT, smem);
+    const int t_out = StLayout::T2 - 2 * (k + 1) * a.bw;
+    const long long n_tiles = (a.n + t_out - 1) / t_out;
+    int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+    if (grid < 1) grid = 1;
+    if (grid > ctx->red.max_blocks) grid = ctx->red.max_blocks;
+    if (b13) k_mrr_steps_band<13><<<grid, MB_NT, smem, ctx->stream>>>(a, ra);
+    else k_mrr_steps_band<0><<<grid, MB_NT, smem, ctx->stream>>>(a, ra);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pk_set_error("fused k-skip steps launch: %s", cudaGetErrorString(e));
+        return PK_ERR_CUDA;
+    }
+    ctx->launches++;
+    ctx->spmvs += k + 1;
+    PkRedArgs rc{};
+    rc.st = ctx->d_state;
+    rc.only_rollback = ctx->ctl_only_rollback;
+    rc.dyn_cj = -1;
+    long long want = (a.n / 2 + 255) / 256;
+    int cgrid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+    if (cgrid < 1) cgrid = 1;
+    k_copy3<<<cgrid, 256, 0, ctx->stream>>>(a.n, t0, r, t1, ar, t2, y, rc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pk_set_error("copy-back launch: %s", cudaGetErrorString(e));
+        return PK_ERR_CUDA;
+    }
+    ctx->launches++;
     return PK_OK;
 }
 

@@ -775,6 +775,12 @@ struct Solve {
             Ctl c(ctx, 0, dyn ? 0 : -1, 0);
             PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
         }
+        // Dense band on one GPU: the k+1 steps, the closing mat-vec and the trip-end reduction in ONE pass over A
+        // (pk_matpow.cu: k_mrr_steps_band) — bit-identical to the step-by-step sequence below.  Scratch: basis slots
+        // that are free once the Gram kernel has run.
+        if (!dyn && pk_mrr_steps_ok(ctx, A, k) &&
+            ((((uintptr_t)x | (uintptr_t)z | (uintptr_t)Ar(0) | (uintptr_t)Ay(0)) & 15) == 0) && (ld % 2 == 0))
+            return pk_launch_mrr_steps(ctx, A, k, Ar(0), Ar(1), Ay(0), z, x, Ar(2), Ar(3), Ay(1), EPI_KS_TRIP_END);
         // The dynamic ping-pong needs the kernel to choose the vector it multiplies, which a host-enqueued halo exchange
         // (ncclSend/Recv of a host-known pointer) cannot follow: only the exchange fused into the SpMV kernel can, so
         // distributed adaptive solves on the NCCL halo path keep update and SpMV separate.

@@ -50,3 +50,16 @@ def test_vector_kernel_register_budgets():
     for pat, cap in ((r"k_cg_xr", 40), (r"k_cg_pE", 32), (r"k_mrr_update", 64)):
         for name, (regs, spill) in _find(res, pat):
             assert regs <= cap, (name, regs, spill)
+
+
+def test_matrix_powers_register_budgets():
+    res = _resources("pk_matpow.cu.log")
+    # dense-band kernel: 384 threads keep two rows of 27 values each in registers (108 registers of values); it must
+    # neither spill nor exceed 65536 / 384 = 170 registers, or the block does not launch
+    for name, (regs, spill) in _find(res, r"k_matpow_bandILi13E"):
+        assert regs <= 168 and spill == 0, (name, regs, spill)
+    for name, (regs, spill) in _find(res, r"k_matpow_bandILi0E"):
+        assert regs <= 168, (name, regs, spill)
+    # general kernel: 640 threads, one row in registers: <= 102 registers (65536 / 640)
+    for name, (regs, spill) in _find(res, r"8k_matpowILb[01]E"):
+        assert regs <= 96, (name, regs, spill)

@@ -267,28 +267,43 @@ def test_matrix_powers_refuses_wide_operators(pk):
     assert op.ctx.lib.pk_matpow(op.ctx.handle, op.handle, 2, _ptr(buf), _ptr(buf)) == -4      # PK_ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("solver,k", [("kskipmrr", 8), ("kskipcg", 4), ("adaptivekskipmrr", 8)])
-def test_solvers_with_and_without_matrix_powers_agree_bitwise(pk, solver, k):
-    """The one-pass basis changes no bit of a solve (run in a subprocess with PK_MATPOW=0 for the reference run)."""
+def _solve_in_subprocess(solver, k, n, env_extra):
     import subprocess
     import sys
-    A = problems.to_scipy(*problems.banded_spd(20000, 13, 0))
-    b = problems.rhs(A.shape[0], "randn", 0)
-    x, info = getattr(pk, solver)(A, b, tol=1e-8, k=k)
+    import tempfile
     code = (
         "import sys, numpy as np, torch\n"
         f"sys.path.insert(0, {ROOT!r})\n"
         "import parallel_krylov_b200 as pk\n"
         "from parallel_krylov_b200 import problems\n"
-        "A = problems.to_scipy(*problems.banded_spd(20000, 13, 0)); b = problems.rhs(A.shape[0], 'randn', 0)\n"
+        f"A = problems.to_scipy(*problems.banded_spd({n}, 13, 0)); b = problems.rhs(A.shape[0], 'randn', 0)\n"
         f"x, info = pk.{solver}(A, b, tol=1e-8, k={k})\n"
         "np.save(sys.argv[1], np.concatenate([x.cpu().numpy(), info['residual'].cpu().numpy()]))\n")
-    import tempfile
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "ref.npy")
-        env = dict(os.environ, PK_MATPOW="0", PK_QUIET="1")
+        env = dict(os.environ, PK_QUIET="1", **env_extra)
         r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        ref = np.load(out)
-    got = np.concatenate([x.cpu().numpy(), info["residual"].cpu().numpy()])
-    assert np.array_equal(got, ref)
+        return np.load(out)
+
+
+@pytest.mark.parametrize("solver,k,n", [("kskipmrr", 8, 20000), ("kskipmrr", 5, 20001), ("kskipmrr", 2, 3001),
+                                        ("kskipcg", 4, 20000), ("adaptivekskipmrr", 8, 20000)])
+def test_solvers_with_and_without_matrix_powers_agree_bitwise(pk, solver, k, n):
+    """The one-pass basis (k_matpow*) changes no bit of a solve, and neither does running the k+1 steps of a k-skip MrR
+    trip as one pass over a dense band (k_mrr_steps_band): same x to the last bit.  Only the trip-end r.r of the fused
+    steps is summed over a different grid, so that residual history agrees to rounding, not bitwise.  Reference runs in
+    subprocesses (the switches are read once per process)."""
+    A = problems.to_scipy(*problems.banded_spd(n, 13, 0))
+    b = problems.rhs(A.shape[0], "randn", 0)
+    x, info = getattr(pk, solver)(A, b, tol=1e-8, k=k)
+    got_x, got_res = x.cpu().numpy(), info["residual"].cpu().numpy()
+    plain = _solve_in_subprocess(solver, k, n, {"PK_MATPOW": "0"})          # k two-chain SpMV passes, step-by-step trip
+    assert np.array_equal(got_x, plain[:n])
+    if solver == "kskipmrr":
+        basis_only = _solve_in_subprocess(solver, k, n, {"PK_KSTEPS": "0"})  # one-pass basis, step-by-step trip
+        assert np.array_equal(basis_only, plain)
+        assert len(got_res) == len(plain) - n
+        np.testing.assert_allclose(got_res, plain[n:], rtol=1e-12)
+    else:
+        assert np.array_equal(got_res, plain[n:])
