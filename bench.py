@@ -105,7 +105,8 @@ def actual_bytes(solver, k, n, nnz, matpow=False):
     gathers counted as one pass): the k-skip basis reads A once for both chains and the step SpMVs consume A·v in
     registers, so a trip makes 2k+1 passes over A, not the 3k+2 of §8d's formula — and k+2 passes when the one-pass
     matrix-powers kernel generates the basis (matpow: the dense-band kernel reads the values only — no column indices,
-    no row pointers; ghost-row re-reads of A are served by L2 and not counted)."""
+    no row pointers; ghost-row re-reads of A are served by L2 and not counted), and 2 passes per trip when the steps of
+    a k-skip MrR trip are fused into one pass as well (dense band, one GPU)."""
     b_a = 12.0 * nnz + 4.0 * (n + 1)                     # one pass over the CSR arrays
     if solver == "cg":                                   # SpMV (A, p, v) + xr (4R 2W) + p (2R 1W)
         return b_a + 16.0 * n + 72.0 * n
@@ -120,9 +121,13 @@ def actual_bytes(solver, k, n, nnz, matpow=False):
         basis = a_once + (2 + 2 * k) * 8.0 * n           # one pass over A, 2 inputs read, 2k level vectors written
     else:
         basis = k * (b_a + 32.0 * n)                     # k two-chain passes: A + 2 gathers + 2 stores each
-    trip = (basis + (k + 1) * b_a                        # + k fused steps + closing SpMV
-            + 8.0 * n * (2 * k + 3)                      # Gram: every basis vector once
-            + first * n + k * fused * n + 16.0 * n)
+    if matpow == "dense" and solver == "kskipmrr" and os.environ.get("PK_KSTEPS", "1") not in ("0", ""):
+        # dense band, one GPU: the k+1 steps + closing mat-vec are ONE pass (k_mrr_steps_band): A's values once, the five
+        # vectors read and written once, then r, A r, y copied home (3R 3W)
+        steps = 8.0 * nnz + 80.0 * n + 48.0 * n
+    else:
+        steps = (k + 1) * b_a + first * n + k * fused * n + 16.0 * n     # k fused steps + closing SpMV
+    trip = basis + steps + 8.0 * n * (2 * k + 3)         # + Gram: every basis vector once
     if solver == "adaptivekskipmrr":
         trip += 16.0 * n                                 # best-x snapshot per trip
     return trip / (k + 1)

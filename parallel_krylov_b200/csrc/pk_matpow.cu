@@ -556,7 +556,9 @@ __global__ void __launch_bounds__(MB_NT, 1) k_mrr_steps_band(StArgs a, PkRedArgs
 __global__ void __launch_bounds__(256) k_copy3(long long n, const double* __restrict__ s0, double* __restrict__ d0,
                                                const double* __restrict__ s1, double* __restrict__ d1,
                                                const double* __restrict__ s2, double* __restrict__ d2, PkRedArgs ra) {
-    if (pk_skip(ra)) return;
+    // NOT gated on the stop flag: the steps kernel in front of it may have raised the flag in its own epilogue, and its
+    // results must still reach home.  (If that kernel was itself skipped the solve is over and the vectors are dead.)
+    if (ra.only_rollback && ra.st->rollback == 0) return;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n2 = n >> 1;
     const double2 *a0 = (const double2*)s0, *a1 = (const double2*)s1, *a2 = (const double2*)s2;
