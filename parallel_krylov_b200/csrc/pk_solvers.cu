@@ -943,7 +943,12 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
     ctx->launches = 0;
     ctx->spmvs = 0;
     // structure probe of the one-pass basis kernel: synchronises once per operator, so it must happen before any capture
-    if (method == PK_KSKIPCG || method == PK_KSKIPMRR || method == PK_ADAPTIVEKSKIPMRR) (void)pk_matpow_ok(ctx, mat, opts->k);
+    if (method == PK_KSKIPCG || method == PK_KSKIPMRR || method == PK_ADAPTIVEKSKIPMRR) {
+        (void)pk_matpow_ok(ctx, mat, opts->k);
+        // the dense-band kernels stage vectors by TMA bulk copies: with a work area or solution vector that is not
+        // 16-byte aligned this operator stays on the general kernels (decided once, before anything is captured)
+        if (mat->mp_dense && ((((uintptr_t)d_work | (uintptr_t)d_x) & 15) != 0 || (mat->ld & 1))) mat->mp_dense = false;
+    }
     PK_CHECK(s.init_state(d_residual, d_nosl, method == PK_ADAPTIVEKSKIPMRR ? d_khistory : nullptr, hist_len));
     int final_k = opts->k;
     int rc = PK_OK;

@@ -307,3 +307,15 @@ def test_solvers_with_and_without_matrix_powers_agree_bitwise(pk, solver, k, n):
         np.testing.assert_allclose(got_res, plain[n:], rtol=1e-12)
     else:
         assert np.array_equal(got_res, plain[n:])
+
+
+def test_matrix_powers_dense_band_rejects_misaligned_level_vectors(pk):
+    """The dense-band kernel stages level 0 by TMA bulk copies: level vectors that are not 16-byte aligned are refused
+    with PK_ERR_ARG (the solvers check their work area up front and stay on the general kernel instead)."""
+    A = problems.to_scipy(*problems.banded_spd(5000, 13, 1))
+    op = pk.Operator.from_any(A)
+    if op.matpow_info(2)["kernel"] != "dense-band":
+        pytest.skip("dense-band kernel switched off")
+    buf = torch.zeros(3 * op.ld + 2, dtype=torch.float64, device="cuda")
+    p = C.c_void_p(buf.data_ptr() + 8)
+    assert op.ctx.lib.pk_matpow(op.ctx.handle, op.handle, 2, p, p) == -2          # PK_ERR_ARG
