@@ -158,6 +158,13 @@ int pk_mat_set_matpow_ext(pk_mat* mat, int half_bw, int max_row_nnz, int64_t row
                           const int64_t* d_halo_global, int64_t rows_above, const int32_t* d_rowptr_above,
                           const int32_t* d_col_above, const double* d_val_above, int64_t rows_below,
                           const int32_t* d_rowptr_below, const int32_t* d_col_below, const double* d_val_below);
+/* Row-partitioned DENSE band: `ext` is a single-GPU CSR operator of the same context over this rank's
+ * [rows_above ghost rows | owned rows | rows_below ghost rows] (copies of the neighbours' boundary rows of A; columns
+ * renumbered from the first of those rows, entries beyond the two ends dropped; both counts even; borrowed, must outlive
+ * `mat`).  pk_solve(PK_KSKIPMRR) then runs each trip on it with the dense-band kernels and ONE ghost-zone exchange of depth
+ * (k+1) bw per trip; the work area needs no more room than pk_work_doubles says, but pk_mat_ld(mat) grows to hold the ghost
+ * zones.  ext = NULL detaches.  PK_ERR_UNSUPPORTED if `ext` is not a dense band of <= 27 diagonals. */
+int pk_mat_set_band_ext(pk_mat* mat, pk_mat* ext, int64_t rows_above, int64_t rows_below);
 /* Longest row and half bandwidth max |global column - global row| of a CSR block given as raw device arrays
  * (h_out[0], h_out[1]; blocking) — col holds GLOBAL indices, row0 is the global index of the block's first row. */
 int pk_csr_band_info(pk_ctx* ctx, int64_t n_rows, int64_t row0, const int32_t* d_rowptr, const int32_t* d_col, int* h_out);

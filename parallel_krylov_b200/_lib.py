@@ -66,6 +66,7 @@ _SIGS = {
     "pk_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "pk_matpow": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "pk_mat_matpow_info": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pk_mat_set_band_ext": (C.c_int, [_P, _P, _I64, _I64]),
     "pk_mat_set_matpow_ext": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _P, _P, _P]),
     "pk_csr_band_info": (C.c_int, [_P, _I64, _I64, _P, _P, C.POINTER(C.c_int)]),
     "pk_dot": (C.c_int, [_P, _I64, _P, _P, _P]),

@@ -300,6 +300,28 @@ int pk_comm_ghost_exchange(pk_ctx* ctx, const double* v0, const double* v1, long
     return PK_OK;
 }
 
+// Ghost zones kept IN the vectors (row-partitioned dense-band trip): own[v] points at the n_loc owned entries of vector v,
+// which has `depth` entries of room on either side; the first / last `depth` owned entries go to the previous / next rank
+// and theirs land in the pads.  One grouped send/recv on the solver's stream (graph-capturable).
+int pk_comm_ghost_exchange_inplace(pk_ctx* ctx, double* const* own, int nvec, long long n_loc, long long depth,
+                                   bool has_prev, bool has_next) {
+    if (!ctx->comm || ctx->n_ranks <= 1 || ctx->nocomm) return PK_OK;
+    const int me = ctx->rank;
+    PK_NCCL(g_nccl.GroupStart());
+    for (int v = 0; v < nvec; ++v) {
+        if (has_prev) {
+            PK_NCCL(g_nccl.Send(own[v], (size_t)depth, ncclDouble, me - 1, ctx->comm->comm, ctx->stream));
+            PK_NCCL(g_nccl.Recv(own[v] - depth, (size_t)depth, ncclDouble, me - 1, ctx->comm->comm, ctx->stream));
+        }
+        if (has_next) {
+            PK_NCCL(g_nccl.Send(own[v] + (n_loc - depth), (size_t)depth, ncclDouble, me + 1, ctx->comm->comm, ctx->stream));
+            PK_NCCL(g_nccl.Recv(own[v] + n_loc, (size_t)depth, ncclDouble, me + 1, ctx->comm->comm, ctx->stream));
+        }
+    }
+    PK_NCCL(g_nccl.GroupEnd());
+    return PK_OK;
+}
+
 int pk_comm_allgather(pk_ctx* ctx, const double* send, double* recv, long long n, cudaStream_t s) {
     if (!ctx->comm || ctx->n_ranks <= 1) {
         if (send != recv) PK_CUDA(cudaMemcpyAsync(recv, send, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));

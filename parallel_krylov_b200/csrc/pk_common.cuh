@@ -161,6 +161,11 @@ struct pk_mat {
     // row-partitioned matrix powers (pk_mat_set_matpow_ext): ghost rows of A from the two neighbours, level-0 ghost inputs
     bool mp_ext = false;
     bool mp_dense = false;   // every row holds its full band: the two-rows-per-thread kernel applies
+    // Row-partitioned dense band: a single-GPU operator over [ghost rows above | owned rows | ghost rows below] (borrowed;
+    // pk_mat_set_band_ext), on which the dense-band kernels run unchanged — whatever the cut ends get wrong travels
+    // bw rows per mat-vec and never reaches the owned rows within a trip.
+    pk_mat* band_ext = nullptr;
+    long long band_ra = 0, band_rb = 0;
     long long mp_row0 = 0, mp_n_global = 0;
     const long long* mp_halo_global = nullptr;                 // borrowed
     const int32_t* mp_g_rowptr[2] = {nullptr, nullptr};        // borrowed: ghost rows above / below (global columns)

@@ -56,7 +56,10 @@ bool pk_matpow_ok(pk_ctx* ctx, pk_mat* m, int k);
 int pk_launch_matpow(pk_ctx* ctx, pk_mat* m, int k, double* base0, double* base1, int dyn);
 bool pk_mrr_steps_ok(pk_ctx* ctx, pk_mat* m, int k);
 int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, double* y, double* z, double* x,
-                        double* t0, double* t1, double* t2, int epi);
+                        double* t0, double* t1, double* t2, int epi, long long own_lo = 0, long long own_hi = -1);
+long long pk_band_ext_depth(pk_ctx* ctx, pk_mat* m, int k);   // > 0: ghost depth of the row-partitioned dense-band trip; 0: not applicable
+int pk_comm_ghost_exchange_inplace(pk_ctx* ctx, double* const* own, int nvec, long long n_loc, long long depth,
+                                   bool has_prev, bool has_next);
 
 // pk_persistent.cu — whole CG loop as one cooperative kernel (small, L2-resident systems)
 int pk_launch_cg_persistent(pk_ctx* ctx, pk_mat* m, double* x, double* r, double* p, double* v, int iters);

@@ -410,6 +410,7 @@ struct StArgs {
     const double* r; const double* ar; const double* y;         // read on whole windows
     double* z; double* x;                                       // in place, finished rows only
     double* r_out; double* ar_out; double* y_out;
+    long long own_lo, own_hi;                                   // rows that may be finished (row-partitioned: the owned ones)
 };
 
 struct StLayout {
@@ -431,13 +432,15 @@ __device__ __forceinline__ void st_issue_window(const StArgs& a, int bw, long lo
     const double* src_a;
     mb_value_run(a.val, a.n, bw, s0, smA, &src_a, &bytes_a);
     const long long f = s0 < 0 ? 0 : s0, e = s0 + T2 > a.n ? a.n : s0 + T2;
+    o0 = o0 < a.own_lo ? a.own_lo : o0;
+    o1 = o1 > a.own_hi ? a.own_hi : o1;
     const long long w_al = f & ~1ll, o_al = o0 & ~1ll;
     // r, A r, y live in ld-padded work vectors: a run may take one element past its end along.  x is the caller's
     // solution vector of exactly n entries: an odd last element of it (and of z, for symmetry) is moved by hand.
     const unsigned bytes_w = (unsigned)(((e - w_al + 1) & ~1ll) * 8);
-    long long ocnt = o1 - o_al;
+    long long ocnt = o1 > o0 ? o1 - o_al : 0;
     if (ocnt & 1) {
-        if (o1 < a.n) ++ocnt;
+        if (o1 < a.own_hi) ++ocnt;
         else { stage[3 * SW + ocnt - 1] = a.z[o1 - 1]; stage[4 * SW + ocnt - 1] = a.x[o1 - 1]; --ocnt; }
     }
     const unsigned bytes_o = (unsigned)(ocnt * 8);
@@ -488,9 +491,11 @@ __global__ void __launch_bounds__(MB_NT, 1) k_mrr_steps_band(StArgs a, PkRedArgs
     const int wA = ((bw & 1) ? H : 0) + tid + (bw >> 1);
     const int wB = (((bw + 1) & 1) ? H : 0) + tid + ((bw + 1) >> 1);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long o0 = tile * t_out;
-        const long long o1 = (o0 + t_out < a.n) ? o0 + t_out : a.n;
-        const long long s0 = o0 - ghost;
+        const long long t0 = tile * t_out;
+        const long long t1 = (t0 + t_out < a.n) ? t0 + t_out : a.n;
+        const long long s0 = t0 - ghost;
+        const long long o0 = t0 < a.own_lo ? a.own_lo : t0;    // finished rows of this window that are also owned
+        const long long o1 = t1 > a.own_hi ? a.own_hi : t1;
         const long long rowA = s0 + 2 * tid, rowB = rowA + 1;
         const long long f = s0 < 0 ? 0 : s0;
         const long long q_al = mb_rowptr(f, a.n, bw) & ~1ll;
@@ -818,9 +823,9 @@ bool pk_mrr_steps_ok(pk_ctx* ctx, pk_mat* m, int k) {
 // r, ar = A r, y, z, x: the vectors of the trip; t0..t2: three scratch vectors (free basis slots).  Runs the k+1 steps,
 // the closing mat-vec and the trip-end epilogue (red[0] = r.r); leaves everything at home.
 int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, double* y, double* z, double* x,
-                        double* t0, double* t1, double* t2, int epi) {
+                        double* t0, double* t1, double* t2, int epi, long long own_lo, long long own_hi) {
     const uintptr_t al = (uintptr_t)r | (uintptr_t)ar | (uintptr_t)y | (uintptr_t)z | (uintptr_t)x | (uintptr_t)t0 | (uintptr_t)t1 | (uintptr_t)t2;
-    if (al & 15) {
+    if ((al & 15) || (own_lo & 1)) {
         pk_set_error("fused k-skip steps stage their vectors by TMA: all vectors must be 16-byte aligned");
         return PK_ERR_ARG;
     }
@@ -828,12 +833,17 @@ int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, do
     a.val = m->val; a.n = m->n_rows; a.bw = m->mp_bw; a.k = k;
     a.r = r; a.ar = ar; a.y = y; a.z = z; a.x = x;
     a.r_out = t0; a.ar_out = t1; a.y_out = t2;
+    a.own_lo = own_lo;
+    a.own_hi = own_hi < 0 ? a.n : own_hi;
     PkRedArgs ra{};
     ra.partials = ctx->red.partials;
     ra.ticket = ctx->red.ticket;
     ra.max_blocks = ctx->red.max_blocks;
     ra.st = ctx->d_state;
     ra.epi = epi;
+    ra.defer = (ctx->n_ranks > 1 && !ctx->d_p2p && !ctx->nocomm) ? 1 : 0;     // NCCL all-reduce + scalar kernel follow
+    ra.p2p = ctx->nocomm ? nullptr : ctx->d_p2p;                              // or: all-reduced inside this kernel
+    ra.ar_n = 1;
     ra.g_off = -1;
     ra.only_rollback = ctx->ctl_only_rollback;
     ra.dyn_cj = -1;
@@ -854,14 +864,17 @@ int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, do
     }
     ctx->launches++;
     ctx->spmvs += k + 1;
+    PK_CHECK(pk_finish_reduce(ctx, 1, epi, -1, 0));
     PkRedArgs rc{};
     rc.st = ctx->d_state;
     rc.only_rollback = ctx->ctl_only_rollback;
     rc.dyn_cj = -1;
-    long long want = (a.n / 2 + 255) / 256;
+    const long long n_own = a.own_hi - a.own_lo;
+    long long want = (n_own / 2 + 255) / 256;
     int cgrid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
     if (cgrid < 1) cgrid = 1;
-    k_copy3<<<cgrid, 256, 0, ctx->stream>>>(a.n, t0, r, t1, ar, t2, y, rc);
+    k_copy3<<<cgrid, 256, 0, ctx->stream>>>(n_own, t0 + a.own_lo, r + a.own_lo, t1 + a.own_lo, ar + a.own_lo,
+                                           t2 + a.own_lo, y + a.own_lo, rc);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         pk_set_error("copy-back launch: %s", cudaGetErrorString(e));
@@ -869,6 +882,58 @@ int pk_launch_mrr_steps(pk_ctx* ctx, pk_mat* m, int k, double* r, double* ar, do
     }
     ctx->launches++;
     return PK_OK;
+}
+
+// ---- row-partitioned dense band -----------------------------------------------------------------------------------------
+// The dense-band kernels run UNCHANGED on a single-GPU operator that covers [ghost rows above | owned rows | ghost rows
+// below] of this rank (the rows cut at its two ends make it a dense band of its own).  The vectors of the solve carry the
+// same ghost zones in pads around their owned part; ONE exchange per trip (depth (k+1) bw of r, A r, y) refreshes them.
+// Whatever the cut ends and the stale zones beyond the exchanged depth get wrong moves bw rows inward per mat-vec: after
+// the k+1 mat-vecs of a trip it has not reached the owned rows, which therefore equal the single-GPU results bit for bit.
+extern "C" int pk_mat_set_band_ext(pk_mat* m, pk_mat* ext, int64_t rows_above, int64_t rows_below) {
+    PK_REQUIRE(m != nullptr, "null operator");
+    if (ext == nullptr) {
+        m->band_ext = nullptr;
+        m->band_ra = m->band_rb = 0;
+        return PK_OK;
+    }
+    PK_REQUIRE(m->distributed && m->ctx == ext->ctx, "the extended operator belongs to a row-partitioned operator of the same context");
+    PK_REQUIRE(!ext->distributed && ext->kind != MAT_DENSE && ext->segs.empty() && ext->n_rows == ext->n_cols, "extended operator: square single-GPU CSR");
+    PK_REQUIRE(rows_above >= 0 && rows_below >= 0 && (rows_above & 1) == 0 && (rows_below & 1) == 0, "ghost row counts must be even");
+    PK_REQUIRE(ext->n_rows == m->n_rows + rows_above + rows_below, "extended operator: owned + ghost rows");
+    pk_ctx* ctx = m->ctx;
+    PK_CUDA(cudaSetDevice(ctx->device));
+    PK_CHECK(band_info(ctx, ext));
+    if (!ext->mp_dense) {
+        pk_set_error("extended operator is not a dense band of <= %d diagonals", MB_DMAX);
+        return PK_ERR_UNSUPPORTED;
+    }
+    // one leading dimension for both: the solve's vectors hold owned rows + both ghost zones
+    long long ld = m->ld > ext->n_rows + m->n_halo ? m->ld : ext->n_rows + m->n_halo;
+    ld = (ld + 31) / 32 * 32;
+    m->ld = ld;
+    ext->ld = ld;
+    m->band_ext = ext;
+    m->band_ra = rows_above;
+    m->band_rb = rows_below;
+    return PK_OK;
+}
+
+long long pk_band_ext_depth(pk_ctx* ctx, pk_mat* m, int k) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PK_BAND_DIST");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || !m->distributed || m->band_ext == nullptr || ctx->comm == nullptr) return 0;
+    pk_mat* ext = m->band_ext;
+    if (!pk_mrr_steps_ok(ctx, ext, k)) return 0;
+    long long depth = (long long)(k + 1) * ext->mp_bw;
+    depth += depth & 1;                                   // pads keep the 16-byte alignment of the owned part
+    const bool has_prev = ctx->rank > 0, has_next = ctx->rank + 1 < ctx->n_ranks;
+    if ((has_prev && m->band_ra < depth) || (has_next && m->band_rb < depth) || m->n_rows < depth) return 0;
+    if ((!has_prev && m->band_ra != 0) || (!has_next && m->band_rb != 0)) return 0;
+    return depth;
 }
 
 extern "C" int pk_mat_matpow_info(pk_ctx* ctx, pk_mat* mat, int k, int* kind, int* window_rows) {

@@ -438,6 +438,10 @@ struct Solve {
     long long n, ld;
     pk_solve_opts o;
     int method;
+    // row-partitioned dense band (pk_matpow.cu): the trip runs on the extended single-GPU operator; every vector of the
+    // solve then has ext_off entries of ghost zone in front of its owned part (and as many behind)
+    pk_mat* ext = nullptr;
+    long long ext_off = 0, ext_depth = 0;
     // graph replay
     cudaGraphExec_t gexec = nullptr;
     long long graph_launches = 0, graph_spmvs = 0;
@@ -762,6 +766,18 @@ struct Solve {
         double* z = vec(2 * k_alloc + 3);
         double* spare = vec(2 * k_alloc + 4);                     // second home of Ar[0] for the fused steps
         const int end_epi = dyn ? EPI_ADAPT_TRIP_END : EPI_KS_TRIP_END;
+        if (ext != nullptr && !dyn) {
+            // ONE exchange per trip: r, A r, y of the neighbours' boundary rows into the pads of the home vectors; then the
+            // single-GPU dense-band kernels on the extended operator (owned rows come out bit-identical to one GPU)
+            const bool has_prev = ctx->rank > 0, has_next = ctx->rank + 1 < ctx->n_ranks;
+            double* own[3] = {Ar(0), Ar(1), Ay(0)};
+            PK_CHECK(pk_comm_ghost_exchange_inplace(ctx, own, 3, n, ext_depth, has_prev, has_next));
+            PK_CHECK(pk_launch_matpow(ctx, ext, k, Ar(1) - ext_off, Ay(0) - ext_off, 0));
+            PK_CHECK(pk_launch_gram(ctx, 0, n, ld, Ar(0), k + 2, Ay(0), k + 1, k + 2, EPI_GRAM_MRR));
+            return pk_launch_mrr_steps(ctx, ext, k, Ar(0) - ext_off, Ar(1) - ext_off, Ay(0) - ext_off, z - ext_off,
+                                       x - ext_off, Ar(2) - ext_off, Ar(3) - ext_off, Ay(1) - ext_off, EPI_KS_TRIP_END,
+                                       ext_off, ext_off + n);
+        }
         if (pk_matpow_ok(ctx, A, k)) {
             // all k levels of both chains in ONE pass over A (pk_matpow.cu); dyn: the kernel reads the current k itself
             PK_CHECK(pk_launch_matpow(ctx, A, k, Ar(1), Ay(0), dyn ? 1 : 0));
@@ -948,6 +964,15 @@ extern "C" int pk_solve(pk_ctx* ctx, int method, pk_mat* mat, const double* d_b,
         // the dense-band kernels stage vectors by TMA bulk copies: with a work area or solution vector that is not
         // 16-byte aligned this operator stays on the general kernels (decided once, before anything is captured)
         if (mat->mp_dense && ((((uintptr_t)d_work | (uintptr_t)d_x) & 15) != 0 || (mat->ld & 1))) mat->mp_dense = false;
+        if (method == PK_KSKIPMRR && opts->basis == 0 && mat->distributed && ((((uintptr_t)d_work | (uintptr_t)d_x) & 15) == 0)) {
+            const long long depth = pk_band_ext_depth(ctx, mat, opts->k);
+            if (depth > 0) {
+                s.ext = mat->band_ext;
+                s.ext_depth = depth;
+                s.ext_off = mat->band_ra;               // rows of the extended operator in front of the owned ones
+                s.work = d_work + s.ext_off;            // the last two work vectors (spare, Chebyshev A r) are unused here
+            }
+        }
     }
     PK_CHECK(s.init_state(d_residual, d_nosl, method == PK_ADAPTIVEKSKIPMRR ? d_khistory : nullptr, hist_len));
     int final_k = opts->k;

@@ -247,6 +247,56 @@ class DistOperator(Operator):
                                             rb, _ptr(keep["below"][0]), _ptr(keep["below"][1]), _ptr(keep["below"][2])),
               "pk_mat_set_matpow_ext")
         self.matpow_ghost_rows = gr
+        self._setup_band_ext(rowptr, colg32, val, keep, gr, rmax, bw, group, world, rank, row0, n_global)
+
+    def _setup_band_ext(self, rowptr, colg32, val, keep, gr, rmax, bw, group, world, rank, row0, n_global):
+        """Row-partitioned DENSE band (csrc/pk_matpow.cu, pk_mat_set_band_ext): a single-GPU operator over
+        [ghost rows above | owned rows | ghost rows below] of this rank, columns renumbered from its first row and cut at
+        its two ends.  The dense-band matrix-powers kernel and the fused k-skip MrR trip then run on it unchanged, with one
+        ghost-zone exchange per trip; the owned rows come out exactly as on one GPU.  All ranks take the same decision."""
+        ctx = self.ctx
+        dev = ctx.torch_device
+        self.band_ext_op = None
+        want = (os.environ.get("PK_BAND_DIST", "1") not in ("0", "") and 2 * bw + 1 <= 27 and rmax <= 27 and gr % 2 == 0)
+        cdev = _comm_device(group)
+        ext_op = None
+        ok = 0
+        if want:
+            try:
+                ra = gr if rank > 0 else 0
+                rb = gr if rank + 1 < world else 0
+                n_ext = self.n_rows + ra + rb
+                first = row0 - ra                                   # global index of the extended operator's first row
+                pieces = []
+                if ra:
+                    pieces.append(keep["above"])
+                pieces.append((rowptr, colg32, val))
+                if rb:
+                    pieces.append(keep["below"])
+                cnt = torch.cat([(p[0][1:] - p[0][:-1]).to(torch.int64) for p in pieces])
+                colx = torch.cat([p[1].to(torch.int64) for p in pieces]) - first
+                valx = torch.cat([p[2] for p in pieces])
+                inside = (colx >= 0) & (colx < n_ext)
+                if not bool(inside.all()):                          # only the outermost ghost rows lose entries
+                    row_of = torch.repeat_interleave(torch.arange(n_ext, device=dev), cnt)
+                    cnt = torch.zeros(n_ext, dtype=torch.int64, device=dev).index_add_(0, row_of[inside], torch.ones_like(row_of[inside]))
+                    colx, valx = colx[inside], valx[inside]
+                    del row_of
+                rp = torch.zeros(n_ext + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(cnt, 0, out=rp[1:])
+                if int(rp[-1]) < 2 ** 31:
+                    ext_op = Operator.from_csr_tensors(rp.to(torch.int32), colx.to(torch.int32).contiguous(),
+                                                       valx.contiguous(), n_ext, ctx)
+                    rc = ctx.lib.pk_mat_set_band_ext(self.handle, ext_op.handle, ra, rb)
+                    ok = 1 if rc == 0 else 0
+            except (PkError, RuntimeError):
+                ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=cdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        if int(t.item()) == 1:
+            self.band_ext_op = ext_op                               # keeps the extended CSR arrays alive
+        else:
+            check(ctx.lib.pk_mat_set_band_ext(self.handle, None, 0, 0), "pk_mat_set_band_ext")
 
     def _open_halo_push(self, group, world, rank, plan):
         """Map the peers' halo receive buffers (CUDA IPC) so that the halo is exchanged by direct NVLink stores from

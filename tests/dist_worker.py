@@ -97,6 +97,11 @@ def main():
     from parallel_krylov_b200._lib import check
     A = mats["band27"]; n = A.shape[0]; base = n // world; lo = rank * base; hi = n if rank == world - 1 else lo + base
     op = pkm.DistOperator.from_any_local(A[lo:hi], None)
+    if os.environ.get("PK_MATPOW", "1") not in ("0", "") and os.environ.get("PK_BAND_DIST", "1") not in ("0", ""):
+        # band27 holds its full band: the k-skip MrR solves above ran their trips on the extended single-GPU operator
+        # (dense-band matrix powers + fused steps, one ghost-zone exchange per trip)
+        if getattr(op, "band_ext_op", None) is None:
+            failures.append(f"[band27 rank {rank}] row-partitioned dense-band operator was not set up")
     if os.environ.get("PK_MATPOW", "1") not in ("0", ""):
         k = 8
         ld = op.ld
