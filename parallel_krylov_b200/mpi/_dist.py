@@ -257,8 +257,14 @@ class DistOperator(Operator):
         ctx = self.ctx
         dev = ctx.torch_device
         self.band_ext_op = None
-        want = (os.environ.get("PK_BAND_DIST", "1") not in ("0", "") and 2 * bw + 1 <= 27 and rmax <= 27 and gr % 2 == 0)
         cdev = _comm_device(group)
+        # a full band of half width bw has n (2 bw + 1) - bw (bw + 1) entries: anything else keeps the general kernels and
+        # never pays for the extended copy (the C side re-checks the structure row by row)
+        tot = torch.tensor([int(val.numel())], dtype=torch.int64, device=cdev)
+        dist.all_reduce(tot, group=group)
+        full = int(tot.item()) == n_global * (2 * bw + 1) - bw * (bw + 1)
+        want = (os.environ.get("PK_BAND_DIST", "1") not in ("0", "") and full and 2 * bw + 1 <= 27 and rmax <= 27
+                and gr % 2 == 0)
         ext_op = None
         ok = 0
         if want:

@@ -63,3 +63,25 @@ def test_matrix_powers_register_budgets():
     # general kernel: 640 threads, one row in registers: <= 102 registers (65536 / 640)
     for name, (regs, spill) in _find(res, r"8k_matpowILb[01]E"):
         assert regs <= 96, (name, regs, spill)
+
+
+def test_dense_band_row_pointer_closed_form_matches_the_generator():
+    """csrc/pk_matpow.cu::mb_rowptr (the dense-band kernels never read A's row pointers: they follow from (n, bw)) —
+    the same formula restated here against the row pointers of problems.banded_spd, incl. the clipped end rows."""
+    import numpy as np
+    from parallel_krylov_b200 import problems
+
+    def mb_rowptr(r, n, bw):
+        q = r * (2 * bw + 1)
+        t = min(r, bw)
+        q -= t * bw - t * (t - 1) // 2
+        m = r - (n - bw)
+        if m > 0:
+            q -= m * (m + 1) // 2
+        return q
+
+    for n, bw in ((27, 13), (28, 13), (100, 1), (101, 2), (1000, 13), (777, 6)):
+        rowptr = np.asarray(problems.banded_spd(n, bw, 0)[0], dtype=np.int64)
+        got = np.array([mb_rowptr(r, n, bw) for r in range(n + 1)], dtype=np.int64)
+        assert np.array_equal(got, rowptr), (n, bw)
+        assert rowptr[-1] == n * (2 * bw + 1) - bw * (bw + 1)           # the count mpi/_dist.py::_setup_band_ext tests
