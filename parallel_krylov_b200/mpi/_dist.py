@@ -126,6 +126,27 @@ def build_halo_plan(rowptr: torch.Tensor, col_global: torch.Tensor, row_offsets:
             "send_idx": send_idx, "interior": interior, "halo_global": ext_cols, "n_rows": n_rows}
 
 
+def band_ext_csr(pieces, first: int, n_ext: int):
+    """CSR of the extended operator of a row-partitioned dense band (csrc/pk_matpow.cu, pk_mat_set_band_ext): `pieces` are
+    consecutive row blocks (rowptr rebased to 0, GLOBAL column indices, values) — ghost rows above, owned rows, ghost rows
+    below; columns are renumbered from `first` (the global index of the first row) and entries outside [0, n_ext) — the
+    ones the outermost ghost rows lose — are dropped.  Pure tensor code (any device): -> (rowptr int64, col int64, val)."""
+    dev = pieces[0][2].device
+    cnt = torch.cat([(p[0][1:] - p[0][:-1]).to(torch.int64) for p in pieces])
+    colx = torch.cat([p[1].to(torch.int64) for p in pieces]) - int(first)
+    valx = torch.cat([p[2] for p in pieces])
+    if cnt.numel() != n_ext:
+        raise PkError("extended operator: the row blocks do not add up")
+    inside = (colx >= 0) & (colx < n_ext)
+    if not bool(inside.all()):
+        row_of = torch.repeat_interleave(torch.arange(n_ext, device=dev), cnt)
+        cnt = torch.zeros(n_ext, dtype=torch.int64, device=dev).index_add_(0, row_of[inside], torch.ones_like(row_of[inside]))
+        colx, valx = colx[inside], valx[inside]
+    rp = torch.zeros(n_ext + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cnt, 0, out=rp[1:])
+    return rp, colx, valx
+
+
 class DistOperator(Operator):
     """A contiguous row block of A on this rank's GPU plus its halo plan."""
 
@@ -279,17 +300,7 @@ class DistOperator(Operator):
                 pieces.append((rowptr, colg32, val))
                 if rb:
                     pieces.append(keep["below"])
-                cnt = torch.cat([(p[0][1:] - p[0][:-1]).to(torch.int64) for p in pieces])
-                colx = torch.cat([p[1].to(torch.int64) for p in pieces]) - first
-                valx = torch.cat([p[2] for p in pieces])
-                inside = (colx >= 0) & (colx < n_ext)
-                if not bool(inside.all()):                          # only the outermost ghost rows lose entries
-                    row_of = torch.repeat_interleave(torch.arange(n_ext, device=dev), cnt)
-                    cnt = torch.zeros(n_ext, dtype=torch.int64, device=dev).index_add_(0, row_of[inside], torch.ones_like(row_of[inside]))
-                    colx, valx = colx[inside], valx[inside]
-                    del row_of
-                rp = torch.zeros(n_ext + 1, dtype=torch.int64, device=dev)
-                torch.cumsum(cnt, 0, out=rp[1:])
+                rp, colx, valx = band_ext_csr(pieces, first, n_ext)
                 if int(rp[-1]) < 2 ** 31:
                     ext_op = Operator.from_csr_tensors(rp.to(torch.int32), colx.to(torch.int32).contiguous(),
                                                        valx.contiguous(), n_ext, ctx)
